@@ -1,0 +1,331 @@
+"""CPU oracle for the AFTER sampling hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+A functional (state-dict driven) restatement, in plain PyTorch CPU ops, of what the
+reference computes on the path SURVEY.md section 8 scopes: ``DenoiserV2.forward``,
+``RectifiedFlow.model_forward`` / ``sample``, ``AutoEncoder.encode`` / ``decode`` and the
+structure encoder ``Encoder1D``.  Every function cites the reference file:line it follows.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may import
+this module; the product package ``after_b200`` never does (it fails loudly when its CUDA
+library is missing).
+
+Parity pinning: the reference ships no tests or golden vectors, so this
+oracle is pinned against outputs of the UNMODIFIED reference modules run in the authoring
+container -- ``tests/golden/make_golden.py`` (committed) imports them from /root/reference under
+the shims in ``tests/golden/ref_shims.py``, loads the same synthetic state dicts, and stores
+input/output fixtures under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this
+file against those fixtures.
+
+The restatement deliberately differs in form from the reference (no nn.Modules, no mask
+tensors built by Python loops, weight-norm folded up front, the CFG batch built by indexing),
+so that agreement with the fixtures is evidence about the algorithm, not about copied code.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+StateDict = Dict[str, Tensor]
+
+
+def _cast(sd: StateDict, dtype) -> StateDict:
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# =============================================================================
+# Denoiser (after/diffusion/networks/transformerv2.py)
+# =============================================================================
+def fourier_features(t: Tensor, n_dims: int, factor: float = 100.0,
+                     max_positions: float = 10000.0) -> Tensor:
+    """[cos(u), sin(u)], u_k = factor * t * max_positions^(-k/(n/2)); transformerv2.py:31-43."""
+    half = n_dims // 2
+    k = torch.arange(half, dtype=torch.float32)
+    freqs = ((1.0 / max_positions)**(k / half)).to(t.dtype)
+    u = torch.outer(t.reshape(-1) * factor, freqs)
+    return torch.cat([u.cos(), u.sin()], dim=1)
+
+
+def band_allowed(seq_len: int, chunk: int, window: int) -> Tensor:
+    """Boolean (L, L) matrix, True where query j may attend key p; transformerv2.py:62-96.
+
+    allowed(j, p)  <=>  p in [c, min(c+chunk, L))  or  (p < c and p >= j - window + 1),
+    with c = chunk * floor(j / chunk)  (SURVEY.md appendix A.2)."""
+    j = torch.arange(seq_len).unsqueeze(1)
+    p = torch.arange(seq_len).unsqueeze(0)
+    c = (j // chunk) * chunk
+    in_chunk = (p >= c) & (p < c + chunk)
+    back = (p < c) & (p >= j - window + 1)
+    return in_chunk | back
+
+
+def rope_rotate(x: Tensor, rot_dim: int = 32, theta: float = 10000.0, offset: int = 0) -> Tensor:
+    """Interleaved-pair RoPE on the first ``rot_dim`` features of (..., L, dh);
+    rotary_embedding.py:143-173, 196-236, 321-362."""
+    L = x.shape[-2]
+    inv = 1.0 / (theta**(torch.arange(0, rot_dim, 2, dtype=torch.float32) / rot_dim))
+    pos = torch.arange(offset, offset + L, dtype=torch.float32)
+    ang = torch.outer(pos, inv).to(x.dtype)  # (L, rot/2), fp32 product like the reference
+    cos, sin = ang.cos(), ang.sin()
+    xe, xo = x[..., 0:rot_dim:2], x[..., 1:rot_dim:2]
+    re = xe * cos - xo * sin
+    ro = xo * cos + xe * sin
+    rot = torch.stack([re, ro], dim=-1).flatten(-2)
+    return torch.cat([rot, x[..., rot_dim:]], dim=-1)
+
+
+def denoiser_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Tensor,
+                     time_cond: Tensor, taps: Optional[dict] = None) -> Tensor:
+    """``DenoiserV2.forward`` offline path (max_cache_size = 0); transformerv2.py:517-543,
+    437-457, 340-362, 190-236.  x (N,C,T), time (N,)|(N,1,1)|(N,1,T), cond (N,zt),
+    time_cond (N,zs,T) -> (N,C,T)."""
+    dt = x.dtype
+    sd = _cast(sd, dt)
+    D, H, dh = cfg.embed_dim, cfg.n_heads, cfg.head_dim
+    if time.dim() > 1:
+        time = time[..., 0]  # transformerv2.py:524-528
+    time = time.reshape(-1).to(dt)
+    N, _, T = x.shape
+
+    emb_in = torch.cat([
+        fourier_features(time, cfg.noise_embed_dims, cfg.fourier_factor, cfg.fourier_max_positions),
+        cond
+    ], dim=-1)
+    feat = F.linear(F.gelu(F.linear(emb_in, sd["embedding.0.weight"], sd["embedding.0.bias"])),
+                    sd["embedding.2.weight"], sd["embedding.2.bias"])  # (N, D)
+
+    tb = "denoiser_trans_block."
+    h = F.gelu(
+        F.linear(x.transpose(1, 2), sd[tb + "patchify_and_embed.1.weight"],
+                 sd[tb + "patchify_and_embed.1.bias"]))  # (N, T, D)
+    tc = F.gelu(
+        F.linear(time_cond.transpose(1, 2), sd[tb + "patchify_and_embed_tcond.1.weight"],
+                 sd[tb + "patchify_and_embed_tcond.1.bias"]))  # (N, T, zs)
+
+    allowed = band_allowed(T, cfg.attention_chunk_size, cfg.local_attention_size)
+    bias = torch.zeros(T, T, dtype=dt).masked_fill(~allowed, float("-inf"))
+    if taps is not None:
+        taps["features"] = feat
+        taps["h0"] = h
+
+    for i in range(cfg.n_layers):
+        p = f"{tb}decoder_blocks.{i}."
+        # AdaLN on the per-frame structure condition (transformerv2.py:345-349)
+        a_t, b_t = F.linear(tc, sd[p + "tcond_linear.weight"], sd[p + "tcond_linear.bias"]).chunk(2, -1)
+        h = F.layer_norm(h, (D, )) * (1 + a_t) + b_t
+        # banded rotary self-attention, no output projection (transformerv2.py:351, 190-236, 267)
+        y = F.layer_norm(h, (D, ), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        q, k, v = F.linear(y, sd[p + "self_attention.qkv_linear.weight"]).chunk(3, dim=2)
+        q, k, v = (z.reshape(N, T, H, dh).transpose(1, 2) for z in (q, k, v))
+        q = rope_rotate(q, cfg.rotary_dim, cfg.rotary_theta)
+        k = rope_rotate(k, cfg.rotary_dim, cfg.rotary_theta)
+        s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh) + bias
+        a = torch.matmul(torch.softmax(s, dim=-1), v)
+        h = h + a.transpose(1, 2).reshape(N, T, D)
+        # AdaLN on the global (time, timbre) features (transformerv2.py:354-358)
+        a_c, b_c = F.linear(feat, sd[p + "linear.weight"], sd[p + "linear.bias"]).chunk(2, -1)
+        h = F.layer_norm(h, (D, )) * (1 + a_c.unsqueeze(1)) + b_c.unsqueeze(1)
+        # MLP (transformerv2.py:361, 275-280)
+        y = F.layer_norm(h, (D, ), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+        y = F.gelu(F.linear(y, sd[p + "mlp.mlp.0.weight"], sd[p + "mlp.mlp.0.bias"]))
+        h = h + F.linear(y, sd[p + "mlp.mlp.2.weight"], sd[p + "mlp.mlp.2.bias"])
+        if taps is not None:
+            taps[f"h{i + 1}"] = h
+
+    out = F.linear(h, sd[tb + "out_proj.0.weight"], sd[tb + "out_proj.0.bias"])
+    return out.transpose(1, 2)
+
+
+# =============================================================================
+# Rectified-flow sampler (after/diffusion/model.py)
+# =============================================================================
+CFG_AUDIO = 0  # rows: (cond, tc) / (drop, tc) / (drop, drop); factor = g_t / max(g_s, clamp)
+CFG_MIDI = 1  # rows: (cond, tc) / (cond, drop) / (drop, drop); factor = g_s / max(g_t, clamp)
+
+
+def model_forward(sd, cfg, x, time, cond, time_cond, guidance_timbre: float,
+                  guidance_structure: float, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
+                  clamp: float = 0.01) -> Tensor:
+    """3-way classifier-free-guidance evaluation; model.py:721-761 (audio variant) and
+    after_scripts/export_midi.py:322-360 (midi variant, clamp 0.1)."""
+    B = x.shape[0]
+    idx = torch.arange(B).repeat(3)
+    drop_c = torch.full_like(cond, drop_value)
+    drop_t = torch.full_like(time_cond, drop_value)
+    if cfg_variant == CFG_AUDIO:
+        conds = torch.cat([cond, drop_c, drop_c])
+        tconds = torch.cat([time_cond, time_cond, drop_t])
+        g_first, g_second = guidance_timbre, guidance_structure
+    else:
+        conds = torch.cat([cond, cond, drop_c])
+        tconds = torch.cat([time_cond, drop_t, drop_t])
+        g_first, g_second = guidance_structure, guidance_timbre
+    t = time.reshape(B, -1)[:, 0]
+    d = denoiser_forward(sd, cfg, x[idx], t[idx], conds, tconds)
+    d_full, d_mid, d_none = d[:B], d[B:2 * B], d[2 * B:]
+    total = 0.5 * (guidance_structure + guidance_timbre)
+    factor = g_first / max(g_second, clamp)
+    return d_none + total * (d_mid + factor * (d_full - d_mid) - d_none)
+
+
+@torch.no_grad()
+def sample(sd, cfg, x0, cond, time_cond, nb_steps: int, guidance_timbre: float = 1.0,
+           guidance_structure: float = 1.0, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
+           clamp: float = 0.01) -> Tensor:
+    """Fixed-step Euler integration of the velocity field on t_i = i / N; model.py:763-785."""
+    x = x0
+    B = x0.shape[0]
+    ts = torch.linspace(0, 1, nb_steps + 1)[:-1]  # fp32 grid, exactly as the reference builds it
+    dt = 1 / nb_steps
+    for t in ts:
+        tt = t.to(x.dtype).reshape(1).repeat(B)
+        x = x + model_forward(sd, cfg, x, tt, cond, time_cond, guidance_timbre,
+                              guidance_structure, drop_value, cfg_variant, clamp) * dt
+    return x
+
+
+# =============================================================================
+# Codec (after/autoencoder/networks/SimpleNetsStream.py, pqmf.py, core.py)
+# =============================================================================
+def fold_weight_norm(sd: StateDict, prefix: str) -> Tensor:
+    """w = g * v / ||v||, norm over all dims but 0 (torch.nn.utils.weight_norm, dim=0);
+    SimpleNetsStream.py:84-92."""
+    v, g = sd[prefix + ".weight_v"], sd[prefix + ".weight_g"]
+    n = v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+    return v * (g / n)
+
+
+def same_padding(kernel: int, dilation: int = 1, causal: bool = False):
+    """cached_conv.get_padding (acids-ircam/cached_conv >= 2.5.0, un-vendored; semantics restated
+    from the reference call sites SimpleNetsStream.py:45,177,453,590 and SURVEY.md section 8c)."""
+    if kernel == 1:
+        return (0, 0)
+    p = (kernel - 1) * dilation + 1
+    if causal:
+        return (p // 2 + (p - 1) // 2, 0)
+    return ((p - 1) // 2, p // 2)
+
+
+def snake_beta(x: Tensor, alpha: Tensor, beta: Tensor) -> Tensor:
+    """x + sin^2(alpha x) / (beta + 1e-9), per channel; core.py:217-218, 250-258."""
+    a = alpha.reshape(1, -1, 1)
+    b = beta.reshape(1, -1, 1)
+    return x + torch.sin(x * a)**2 / (b + 1e-9)
+
+
+def _wn_conv(sd, prefix, x, stride=1, dilation=1, pad=None, causal=False):
+    w = fold_weight_norm(sd, prefix)
+    if pad is None:
+        pad = same_padding(w.shape[-1], dilation, causal)
+    return F.conv1d(F.pad(x, pad), w, sd[prefix + ".bias"], stride=stride, dilation=dilation)
+
+
+def _conv_block(sd, prefix, x, dilation=1, groups=8):
+    """GroupNorm(min(C,8)) -> SnakeBeta -> conv; SimpleNetsStream.py:150-194."""
+    C = x.shape[1]
+    y = F.group_norm(x, min(C, groups), sd[prefix + ".net.0.gn.weight"], sd[prefix + ".net.0.gn.bias"],
+                     eps=1e-5)
+    y = snake_beta(y, sd[prefix + ".net.1.alpha"], sd[prefix + ".net.1.beta"])
+    return _wn_conv(sd, prefix + ".net.2", y, dilation=dilation)
+
+
+def _resnet(sd, prefix, x, dilation=1, groups=8):
+    """block2(block1(x)) + skip(x); SimpleNetsStream.py:197-254."""
+    y = _conv_block(sd, prefix + ".net.branches.0.0", x, dilation, groups)
+    y = _conv_block(sd, prefix + ".net.branches.0.1", y, 1, 8)
+    skip_key = prefix + ".net.branches.1.weight_v"
+    skip = _wn_conv(sd, prefix + ".net.branches.1", x) if skip_key in sd else x
+    return y + skip
+
+
+def pqmf_analysis(sd, x: Tensor) -> Tensor:
+    """(B,1,S) -> (B,M,S/M): strided FIR bank then negate odd bands at even frames;
+    pqmf.py:16-20, 263-271, 286-290."""
+    w = sd["pqmf.forward_conv.weight"]
+    M = w.shape[0]
+    y = F.conv1d(F.pad(x, same_padding(w.shape[-1])), w, stride=M)
+    sign = torch.ones(M, y.shape[-1], dtype=y.dtype)
+    sign[1::2, ::2] = -1
+    return y * sign
+
+
+def pqmf_synthesis(sd, x: Tensor) -> Tensor:
+    """(B,M,T) -> (B,1,M*T); pqmf.py:292-301."""
+    w = sd["pqmf.inverse_conv.weight"]
+    M = w.shape[0]
+    sign = torch.ones(M, x.shape[-1], dtype=x.dtype)
+    sign[1::2, ::2] = -1
+    y = F.conv1d(F.pad(x * sign, same_padding(w.shape[-1])), w) * M
+    y = y.flip(1)  # band order reversed
+    return y.transpose(1, 2).reshape(x.shape[0], 1, -1)  # sample m of frame t -> t*M + m
+
+
+def ae_encode(sd: StateDict, cfg, audio: Tensor) -> Tensor:
+    """``AutoEncoder.encode`` (bottleneck = identity at inference); SimpleNetsStream.py:918-941,
+    400-459, 301-341, 753-760."""
+    sd = _cast(sd, audio.dtype)
+    x = pqmf_analysis(sd, audio) if cfg.pqmf_bands > 1 else audio
+    x = _resnet(sd, "encoder.net.0", x, 1, cfg.resnet_groups)
+    nb = cfg.num_blocks
+    for i, f in enumerate(cfg.factors):
+        p = f"encoder.net.{i + 1}"
+        for j in range(nb):
+            x = _resnet(sd, f"{p}.net.{j}", x, cfg.dilations[j], cfg.resnet_groups)
+        x = snake_beta(x, sd[f"{p}.net.{nb}.alpha"], sd[f"{p}.net.{nb}.beta"])
+        x = _wn_conv(sd, f"{p}.net.{nb + 1}", x, stride=f, pad=same_padding(2 * f))
+    n = len(cfg.factors)
+    x = snake_beta(x, sd[f"encoder.net.{n + 1}.alpha"], sd[f"encoder.net.{n + 1}.beta"])
+    return _wn_conv(sd, f"encoder.net.{n + 2}", x)
+
+
+def ae_decode(sd: StateDict, cfg, z: Tensor) -> Tensor:
+    """``AutoEncoder.decode``; SimpleNetsStream.py:943-954, 552-651, 344-384, 51-70."""
+    sd = _cast(sd, z.dtype)
+    x = _wn_conv(sd, "decoder.net.0", z)
+    nb = cfg.num_blocks
+    for i, f in enumerate(cfg.factors[::-1]):
+        p = f"decoder.net.{i + 1}"
+        x = snake_beta(x, sd[f"{p}.net.0.alpha"], sd[f"{p}.net.0.beta"])
+        w = fold_weight_norm(sd, f"{p}.net.1")  # (in, out, k): norm per *input* channel
+        x = F.conv_transpose1d(x, w, sd[f"{p}.net.1.bias"], stride=f, padding=f // 2)
+        for j in range(nb):
+            x = _resnet(sd, f"{p}.net.{2 + j}", x, cfg.dilations[j], cfg.resnet_groups)
+    x = _conv_block(sd, "decoder.synth.branches.0.net.0", x, 1, cfg.resnet_groups)
+    x = _conv_block(sd, "decoder.synth.branches.0.net.1", x, 1, 8)
+    if cfg.use_loudness:
+        half = x.shape[1] // 2
+        x = x[:, :half] * torch.sigmoid(x[:, half:])
+    return pqmf_synthesis(sd, x) if cfg.pqmf_bands > 1 else x
+
+
+# =============================================================================
+# Structure encoder (after/diffusion/networks/encoder.py)
+# =============================================================================
+def _bn_eval(sd, prefix, x, eps=1e-5):
+    s = sd[prefix + ".weight"] / torch.sqrt(sd[prefix + ".running_var"] + eps)
+    return x * s.reshape(1, -1, 1) + (sd[prefix + ".bias"] - sd[prefix + ".running_mean"] * s).reshape(1, -1, 1)
+
+
+def _v2_conv_block(sd, prefix, x, causal):
+    """x + conv(SiLU(BN(conv(SiLU(BN(x)))))) (dropout off); encoder.py:25-71."""
+    y = F.silu(_bn_eval(sd, prefix + ".net.branches.0.0", x))
+    y = _wn_conv(sd, prefix + ".net.branches.0.2", y, causal=causal)
+    y = F.silu(_bn_eval(sd, prefix + ".net.branches.0.3", y))
+    y = _wn_conv(sd, prefix + ".net.branches.0.6", y, causal=causal)
+    return x + y
+
+
+def encoder1d_forward(sd: StateDict, cfg, z: Tensor) -> Tensor:
+    """``Encoder1D.forward`` with all ratios == 1; encoder.py:273-298, 74-113, 116-237."""
+    sd = _cast(sd, z.dtype)
+    x = z
+    n = len(cfg.channels)
+    assert all(r == 1 for r in cfg.ratios), "oracle covers the shipped (ratio 1) configuration"
+    for i in range(n):
+        x = _v2_conv_block(sd, f"net.{i}.net.0", x, cfg.causal)
+        x = _wn_conv(sd, f"net.{i}.net.1", x)
+    x = _v2_conv_block(sd, f"net.{n}", x, cfg.causal)
+    return torch.tanh(x) if cfg.use_tanh else x
