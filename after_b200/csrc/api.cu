@@ -1,0 +1,347 @@
+// C ABI of libafter_b200.so (see include/after_b200.h).  Everything here is argument checking, error
+// translation and stream plumbing; the work lives in denoiser.cuh / codec.cuh / encoder1d.cuh.
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "codec.cuh"
+#include "context.cuh"
+#include "denoiser.cuh"
+
+namespace after {
+std::atomic<int64_t> g_launches{0};
+}
+
+using namespace after;
+
+struct after_ctx {
+  after_config cfg{};
+  int device = 0;
+  int precision = -1;  // -1: weights not finalized
+  TensorMap tensors[4];
+  Arena arena;
+  StreamBridge bridge;
+  Denoiser denoiser;
+  Codec codec;
+  StructureEncoder structure;
+  bool have_codec = false, have_structure = false;
+  // pinned staging for the *_host entry points
+  float* pin = nullptr;
+  size_t pin_floats = 0;
+  float* dev_io = nullptr;
+  size_t dev_io_floats = 0;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename F>
+int guarded(after_handle h, F&& f) {
+  try {
+    if (!h) throw Error(AFTER_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    f();
+    return AFTER_OK;
+  } catch (const Error& e) {
+    (h ? h->err : g_err) = e.what();
+    cudaGetLastError();  // clear a sticky-free error so the next call starts clean
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    (h ? h->err : g_err) = "out of host memory";
+    return AFTER_ENOMEM;
+  } catch (const std::exception& e) {
+    (h ? h->err : g_err) = e.what();
+    return AFTER_EINVAL;
+  }
+}
+
+void require_ready(after_handle h) {
+  AFTER_REQUIRE(h->precision >= 0, AFTER_ESTATE, "after_finalize_weights has not been called on this handle");
+}
+
+void ensure_staging(after_handle h, size_t floats) {
+  if (floats > h->pin_floats) {
+    if (h->pin) cudaFreeHost(h->pin);
+    h->pin = nullptr;
+    AFTER_CUDA_CHECK(cudaMallocHost(&h->pin, floats * sizeof(float)));
+    h->pin_floats = floats;
+  }
+  if (floats > h->dev_io_floats) {
+    if (h->dev_io) cudaFree(h->dev_io);
+    h->dev_io = nullptr;
+    AFTER_CUDA_CHECK(cudaMalloc(&h->dev_io, floats * sizeof(float)));
+    h->dev_io_floats = floats;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int after_abi_version(void) { return AFTER_B200_ABI_VERSION; }
+
+const char* after_build_info(void) {
+  return "libafter_b200 abi=1 arch=sm_100a (tcgen05/TMEM/TMA) nvcc=" AFTER_STR(__CUDACC_VER_MAJOR__) "." AFTER_STR(
+      __CUDACC_VER_MINOR__) " built " __DATE__;
+}
+
+int after_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* after_last_error(after_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int after_create(const after_config* cfg, int device, after_handle* out) {
+  try {
+    AFTER_REQUIRE(cfg && out, AFTER_EINVAL, "null argument");
+    AFTER_REQUIRE(cfg->abi_version == AFTER_B200_ABI_VERSION, AFTER_EINVAL, "after_config.abi_version mismatch");
+    int n = after_device_count();
+    AFTER_REQUIRE(n > 0, AFTER_ECUDA, "no CUDA device visible: libafter_b200 has no CPU fallback");
+    AFTER_REQUIRE(device >= 0 && device < n, AFTER_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    AFTER_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    AFTER_REQUIRE(prop.major == 10, AFTER_ECUDA,
+                  std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                      "; this library contains sm_100a code only");
+    std::unique_ptr<after_ctx> h(new after_ctx());
+    h->cfg = *cfg;
+    h->device = device;
+    DeviceGuard g(device);
+    h->bridge.init();
+    *out = h.release();
+    return AFTER_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return AFTER_EINVAL;
+  }
+}
+
+int after_destroy(after_handle h) {
+  if (!h) return AFTER_OK;
+  {
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    h->denoiser.destroy();
+    h->codec.destroy();
+    h->bridge.destroy();
+    h->arena.release();
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dev_io) cudaFree(h->dev_io);
+  }
+  delete h;
+  return AFTER_OK;
+}
+
+int after_load_tensor(after_handle h, int module, const char* key, const void* data, const int64_t* shape, int ndim,
+                      int dtype) {
+  int ignored = 0;
+  int rc = guarded(h, [&] {
+    AFTER_REQUIRE(h->precision < 0, AFTER_ESTATE, "weights already finalized");
+    AFTER_REQUIRE(module >= 0 && module < 4, AFTER_EINVAL, "unknown module id");
+    AFTER_REQUIRE(key && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 8, AFTER_EINVAL, "bad tensor arguments");
+    const std::string k(key);
+    // buffers the offline path never reads: streaming caches, unused position table, GroupNorm stream pads
+    auto ends_with = [&](const char* s) {
+      size_t n = strlen(s);
+      return k.size() >= n && k.compare(k.size() - n, n, s) == 0;
+    };
+    if (k.find("cache") != std::string::npos || ends_with("precomputed_pos_enc") || ends_with(".pad") ||
+        ends_with("num_batches_tracked") || ends_with("pqmf.hk") || ends_with("pqmf.h")) {
+      ignored = 1;
+      return;
+    }
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const int64_t n = t.numel();
+    t.data.resize((size_t)n);
+    if (dtype == AFTER_DTYPE_F32) memcpy(t.data.data(), data, (size_t)n * 4);
+    else if (dtype == AFTER_DTYPE_F64)
+      for (int64_t i = 0; i < n; ++i) t.data[i] = (float)reinterpret_cast<const double*>(data)[i];
+    else if (dtype == AFTER_DTYPE_I64)
+      for (int64_t i = 0; i < n; ++i) t.data[i] = (float)reinterpret_cast<const int64_t*>(data)[i];
+    else throw Error(AFTER_EINVAL, "unsupported dtype");
+    h->tensors[module][k] = std::move(t);
+  });
+  return rc == AFTER_OK && ignored ? AFTER_IGNORED : rc;
+}
+
+int after_finalize_weights(after_handle h, int precision) {
+  return guarded(h, [&] {
+    AFTER_REQUIRE(h->precision < 0, AFTER_ESTATE, "weights already finalized");
+    AFTER_REQUIRE(precision >= 0 && precision <= 2, AFTER_EINVAL, "unknown precision mode");
+    bool any = false;
+    if (!h->tensors[AFTER_MODULE_DENOISER].empty()) {
+      h->denoiser.finalize(h->cfg, h->tensors[AFTER_MODULE_DENOISER], precision, &h->arena);
+      any = true;
+    }
+    if (!h->tensors[AFTER_MODULE_AUTOENCODER].empty()) {
+      AFTER_REQUIRE(h->cfg.ae_channels > 0, AFTER_EINVAL, "autoencoder tensors loaded but after_config.ae_channels == 0");
+      h->codec.finalize(h->cfg, h->tensors[AFTER_MODULE_AUTOENCODER], precision, &h->arena);
+      h->have_codec = true;
+      any = true;
+    }
+    if (!h->tensors[AFTER_MODULE_STRUCTURE_ENCODER].empty()) {
+      AFTER_REQUIRE(h->cfg.se_n_blocks > 0, AFTER_EINVAL, "structure-encoder tensors loaded but after_config.se_n_blocks == 0");
+      h->structure.finalize(h->cfg, h->tensors[AFTER_MODULE_STRUCTURE_ENCODER], precision, &h->arena);
+      h->have_structure = true;
+      any = true;
+    }
+    AFTER_REQUIRE(any, AFTER_EMISSING, "no tensors were loaded");
+    for (auto& m : h->tensors) m.clear();  // host copies are no longer needed
+    h->precision = precision;
+  });
+}
+
+int after_denoiser_forward(after_handle h, const float* x, const float* time, const float* cond, const float* time_cond,
+                           float* out, int N, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.forward(x, time, cond, time_cond, out, N, T, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_model_forward(after_handle h, const float* x, const float* time, const float* cond, const float* time_cond,
+                        float* out, int B, int T, float guidance_timbre, float guidance_structure, int cfg_variant,
+                        float clamp, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.model_forward(x, time, cond, time_cond, out, B, T, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                              h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_sample(after_handle h, const float* x0, const float* cond, const float* time_cond, float* out, int B, int T,
+                 int nb_steps, float guidance_timbre, float guidance_structure, int cfg_variant, float clamp,
+                 void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x0 && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.sample(x0, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                       h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_sample_host(after_handle h, const float* x0, const float* cond, const float* time_cond, float* out, int B,
+                      int T, int nb_steps, float guidance_timbre, float guidance_structure, int cfg_variant,
+                      float clamp, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x0 && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    AFTER_REQUIRE(B >= 1 && T >= 1, AFTER_EINVAL, "B and T must be >= 1");
+    const Denoiser& d = h->denoiser;
+    const size_t nx = (size_t)B * d.C * T, nc = (size_t)B * d.zt, nt = (size_t)B * d.zs * T;
+    ensure_staging(h, 2 * nx + nc + nt);
+    float* dx = h->dev_io;
+    float* dc = dx + nx;
+    float* dt = dc + nc;
+    float* dout = dt + nt;
+    cudaStream_t st = h->bridge.work;
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(dx, x0, nx * 4, cudaMemcpyHostToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(dc, cond, nc * 4, cudaMemcpyHostToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(dt, time_cond, nt * 4, cudaMemcpyHostToDevice, st));
+    h->denoiser.sample(dx, dc, dt, dout, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp, st);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(out, dout, nx * 4, cudaMemcpyDeviceToHost, st));
+    AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
+    h->bridge.exit(user);
+  });
+}
+
+int after_ae_encode(after_handle h, const float* audio, float* z, int B, int64_t samples, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
+    AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->codec.encode(audio, z, B, samples, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
+    AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->codec.decode(z, audio, B, T, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_structure_encode(after_handle h, const float* z, float* time_cond, int B, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_structure, AFTER_ESTATE, "no structure-encoder weights on this handle");
+    AFTER_REQUIRE(z && time_cond, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->structure.forward(z, time_cond, B, T, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int64_t after_launch_count(after_handle) { return g_launches.load(); }
+
+int64_t after_device_bytes(after_handle h) { return h ? (int64_t)h->arena.bytes : 0; }
+
+int after_ae_ratio(after_handle h) {
+  if (!h || h->cfg.ae_channels <= 0) return 0;
+  int r = h->cfg.ae_pqmf_bands > 0 ? h->cfg.ae_pqmf_bands : 1;
+  for (int i = 0; i < h->cfg.ae_n_stages; ++i) r *= h->cfg.ae_factors[i];
+  return r;
+}
+
+int after_debug_gemm(after_handle h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                     int precision, void* stream) {
+  return guarded(h, [&] {
+    AFTER_REQUIRE(A && W && C, AFTER_EINVAL, "null tensor pointer");
+    AFTER_REQUIRE(M >= 1 && N >= 1 && K >= 1, AFTER_EINVAL, "bad GEMM shape");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    debug_gemm(A, W, bias, C, M, N, K, precision, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// Row-wise (one warp per token) kernels of the DenoiserV2 forward, plus the small per-call kernels.
+// Reference semantics: after/diffusion/networks/transformerv2.py (line numbers in each kernel header).
+#pragma once
+#include "common.cuh"
+
+namespace after {
+
+// -------------------------------------------------------------------------------------------
+// Output of a row-wise kernel that feeds a GEMM: fp32 (SIMT path) or bf16 hi/lo split (tcgen05 path).
+// -------------------------------------------------------------------------------------------
+struct RowOperandOut {
+  float* f32 = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+};
+
+__device__ __forceinline__ void store_operand4(const RowOperandOut& o, size_t off, float4 v) {
+  if (o.f32) *reinterpret_cast<float4*>(o.f32 + off) = v;
+  if (o.hi) {
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(o.hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    if (o.lo) *reinterpret_cast<uint2*>(o.lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  }
+}
+
+// LayerNorm statistics of a row distributed over a warp (NV values per lane), biased variance, eps inside sqrt.
+template <int NV>
+__device__ __forceinline__ void row_stats(const float (&x)[NV], int D, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += x[i];
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { float d = x[i] - mean; q = fmaf(d, d, q); }
+  float var = warp_sum(q) / (float)D;
+  rstd = 1.0f / sqrtf(var + 1e-5f);
+}
+
+// Sequence -> AdaLN table row mapping.  For sequence n and frame t the per-frame (alpha_t, beta_t) row
+// is t_row0[n] + t * t_stride[n]  (stride 0 = the constant "dropped" row), the per-sequence
+// (alpha_c, beta_c) row is c_row[n].
+struct SeqMap {
+  const int* src_seq;   // layer-0 input sequence (the three CFG rows share the patch-embedded x)
+  const int* t_row0;
+  const int* t_stride;
+  const int* c_row;
+};
+
+// -------------------------------------------------------------------------------------------
+// h <- LN0(h) * (1 + alpha_t) + beta_t ;  a <- LN1(h) * g1 + b1            (transformerv2.py:345-351)
+// lane layout: lane owns float4 groups  e = (i*32 + lane)*4 .. +3,  i < NV/4
+// -------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+adaln_t_ln1_kernel(const float* h_in, float* h_out, RowOperandOut a_out,
+                   const float* __restrict__ adaT, int ada_ld, int ada_off, SeqMap map, int use_src,
+                   const float* __restrict__ g1, const float* __restrict__ b1, int n_rows, int T) {
+  constexpr int D = NV * 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int n = row / T, t = row - n * T;
+  const int src_row = use_src ? map.src_seq[n] * T + t : row;
+  const float* hp = h_in + (size_t)src_row * D;
+  const float* ap = adaT + (size_t)(map.t_row0[n] + t * map.t_stride[n]) * ada_ld + ada_off;
+
+  float x[NV];
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    float4 v = *reinterpret_cast<const float4*>(hp + (i * 32 + lane) * 4);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  float mean, rstd;
+  row_stats<NV>(x, D, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    float4 al = *reinterpret_cast<const float4*>(ap + e);
+    float4 be = *reinterpret_cast<const float4*>(ap + D + e);
+    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
+    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
+    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
+    *reinterpret_cast<float4*>(h_out + (size_t)row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  }
+  row_stats<NV>(x, D, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    float4 g = *reinterpret_cast<const float4*>(g1 + e);
+    float4 b = *reinterpret_cast<const float4*>(b1 + e);
+    float4 o;
+    o.x = (x[4 * i + 0] - mean) * rstd * g.x + b.x;
+    o.y = (x[4 * i + 1] - mean) * rstd * g.y + b.y;
+    o.z = (x[4 * i + 2] - mean) * rstd * g.z + b.z;
+    o.w = (x[4 * i + 3] - mean) * rstd * g.w + b.w;
+    store_operand4(a_out, (size_t)row * D + e, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Banded rotary attention + residual + AdaLN-c + LN3                      (transformerv2.py:190-236, 351-361)
+//   keys of query t: [ks, ce),  c0 = 4*floor(t/4), ce = min(c0+chunk, T), ks = min(c0, max(0, t-w+1))
+//   (full attention inside the 4-chunk, sliding window of w counted back from the query)
+//   h <- h + softmax(q k^T / sqrt(64)) v ;  h <- LN2(h) * (1 + alpha_c) + beta_c ;  a <- LN3(h) * g3 + b3
+// q/k already carry the rotary embedding (QKV GEMM epilogue).  One warp per token; for head hd the lane
+// owns dims (2*lane, 2*lane+1) of that head, i.e. elements hd*64 + 2*lane + {0,1} of the row.
+// -------------------------------------------------------------------------------------------
+template <int NH, int MAXK>
+__global__ void __launch_bounds__(128)
+attn_adaln_c_ln3_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
+                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
+                        const float* __restrict__ g3, const float* __restrict__ b3, int n_rows, int T,
+                        int chunk, int window) {
+  constexpr int D = NH * 64;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int n = row / T, t = row - n * T;
+  const int c0 = (t / chunk) * chunk;
+  const int ce = min(c0 + chunk, T);
+  const int ks = min(c0, max(0, t - window + 1));
+  const int nk = ce - ks;  // <= chunk + window - 1 <= MAXK
+  const float* qrow = qkv + (size_t)row * (3 * D);
+  const float* kbase = qkv + (size_t)(n * T + ks) * (3 * D) + D;
+  const float* vbase = kbase + D;
+  const float scale = 0.125f;  // 1/sqrt(64)
+
+  float x[NH * 2];
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    const float2 q = *reinterpret_cast<const float2*>(qrow + hd * 64 + 2 * lane);
+    float s[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      if (j < nk) {
+        const float2 k = *reinterpret_cast<const float2*>(kbase + (size_t)j * (3 * D) + hd * 64 + 2 * lane);
+        s[j] = fmaf(q.x, k.x, q.y * k.y);
+      } else {
+        s[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) s[j] = warp_sum(s[j]) * scale;
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) if (j < nk) m = fmaxf(m, s[j]);
+    float l = 0.f;
+    float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      if (j < nk) {
+        const float p = expf(s[j] - m);
+        l += p;
+        const float2 v = *reinterpret_cast<const float2*>(vbase + (size_t)j * (3 * D) + hd * 64 + 2 * lane);
+        o.x = fmaf(p, v.x, o.x);
+        o.y = fmaf(p, v.y, o.y);
+      }
+    }
+    const float inv = 1.0f / l;
+    const float2 r = *reinterpret_cast<const float2*>(h + (size_t)row * D + hd * 64 + 2 * lane);
+    x[2 * hd] = r.x + o.x * inv;
+    x[2 * hd + 1] = r.y + o.y * inv;
+  }
+  float mean, rstd;
+  row_stats<NH * 2>(x, D, mean, rstd);
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    const int e = hd * 64 + 2 * lane;
+    const float2 al = *reinterpret_cast<const float2*>(ap + e);
+    const float2 be = *reinterpret_cast<const float2*>(ap + D + e);
+    x[2 * hd] = (x[2 * hd] - mean) * rstd * (1.f + al.x) + be.x;
+    x[2 * hd + 1] = (x[2 * hd + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    *reinterpret_cast<float2*>(h + (size_t)row * D + e) = make_float2(x[2 * hd], x[2 * hd + 1]);
+  }
+  row_stats<NH * 2>(x, D, mean, rstd);
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    const int e = hd * 64 + 2 * lane;
+    const float2 g = *reinterpret_cast<const float2*>(g3 + e);
+    const float2 b = *reinterpret_cast<const float2*>(b3 + e);
+    const float ox = (x[2 * hd] - mean) * rstd * g.x + b.x;
+    const float oy = (x[2 * hd + 1] - mean) * rstd * g.y + b.y;
+    const size_t off = (size_t)row * D + e;
+    if (a_out.f32) *reinterpret_cast<float2*>(a_out.f32 + off) = make_float2(ox, oy);
+    if (a_out.hi) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(ox, h0, l0); split_bf16(oy, h1, l1);
+      *reinterpret_cast<uint32_t*>(a_out.hi + off) = pack_bf16x2(h0, h1);
+      if (a_out.lo) *reinterpret_cast<uint32_t*>(a_out.lo + off) = pack_bf16x2(l0, l1);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// patchify_and_embed: h0[(b,t), :] = GELU(W_in x[b, :, t] + b_in)          (transformerv2.py:387-391, 440)
+// x channel-first (B, C, T); Wt = W_in^T stored [C][D].  Block: 32 frames of one stream, 256 threads.
+// -------------------------------------------------------------------------------------------
+template <int TPB_FRAMES>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
+                   float* __restrict__ h0, int C, int T, int D) {
+  extern __shared__ float xs[];  // [C][TPB_FRAMES]
+  const int b = blockIdx.y, t0 = blockIdx.x * TPB_FRAMES;
+  for (int i = threadIdx.x; i < C * TPB_FRAMES; i += blockDim.x) {
+    int c = i / TPB_FRAMES, tt = i % TPB_FRAMES;
+    xs[i] = (t0 + tt < T) ? x[((size_t)b * C + c) * T + t0 + tt] : 0.f;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc[TPB_FRAMES];
+    const float bv = bias[d];
+#pragma unroll
+    for (int tt = 0; tt < TPB_FRAMES; ++tt) acc[tt] = bv;
+    for (int c = 0; c < C; ++c) {
+      const float w = Wt[(size_t)c * D + d];
+#pragma unroll
+      for (int tt = 0; tt < TPB_FRAMES; ++tt) acc[tt] = fmaf(xs[c * TPB_FRAMES + tt], w, acc[tt]);
+    }
+#pragma unroll
+    for (int tt = 0; tt < TPB_FRAMES; ++tt)
+      if (t0 + tt < T) h0[((size_t)b * T + t0 + tt) * D + d] = gelu_erf(acc[tt]);
+  }
+}
+
+// time_cond (B, zs, T) channel-first -> tc_emb[(b,t), :] = GELU(W_tc tc[b,:,t] + b_tc); last row (index B*T)
+// is the embedding of the constant drop vector.                          (transformerv2.py:393-398, 448-449)
+__global__ void tcond_embed_kernel(const float* __restrict__ tc, const float* __restrict__ W,
+                                   const float* __restrict__ bias, float* __restrict__ out, int B, int zs, int T,
+                                   float drop_value) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = B * T + 1;
+  if (idx >= rows * zs) return;
+  const int r = idx / zs, o = idx % zs;
+  float acc = bias[o];
+  if (r < B * T) {
+    const int b = r / T, t = r % T;
+    for (int c = 0; c < zs; ++c) acc = fmaf(tc[((size_t)b * zs + c) * T + t], W[o * zs + c], acc);
+  } else {
+    for (int c = 0; c < zs; ++c) acc = fmaf(drop_value, W[o * zs + c], acc);
+  }
+  out[(size_t)r * zs + o] = gelu_erf(acc);
+}
+
+// Fourier time features ++ timbre condition -> rows of the embedding-MLP input   (transformerv2.py:31-43, 530-535)
+//   E[r, k] = cos(u_k), E[r, half+k] = sin(u_k), u_k = (factor * t_r) * freq_k ; E[r, 2*half + j] = cond_r[j]
+// row r = s * n_cls + c : time of step s (times[s] or per-row times), condition class c (c == n_cond -> drop vector)
+__global__ void fourier_concat_kernel(const float* __restrict__ times, int times_per_row,
+                                      const float* __restrict__ cond, int n_cond, int zt,
+                                      const float* __restrict__ freqs, int half, float factor, float drop_value,
+                                      float* __restrict__ E, int rows, int n_cls) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = 2 * half + zt;
+  if (idx >= rows * ld) return;
+  const int r = idx / ld, k = idx % ld;
+  const int s = r / n_cls, c = r % n_cls;
+  const float t = times_per_row ? times[r] : times[s];
+  float v;
+  if (k < 2 * half) {
+    const float u = (t * factor) * freqs[k % half];
+    v = (k < half) ? cosf(u) : sinf(u);
+  } else {
+    v = (c < n_cond) ? cond[c * zt + (k - 2 * half)] : drop_value;
+  }
+  E[idx] = v;
+}
+
+__global__ void rope_table_kernel(float2* __restrict__ tab, const float* __restrict__ inv_freq, int T, int half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * half) return;
+  const int p = idx / half, j = idx % half;
+  const float ang = (float)p * inv_freq[j];
+  tab[idx] = make_float2(cosf(ang), sinf(ang));
+}
+
+// -------------------------------------------------------------------------------------------
+// CFG combine (+ optional Euler update).   proj: [3B*T, C] token-major out_proj results.
+//   d = d_none + g * (d_mid + f * (d_full - d_mid) - d_none)              (model.py:751-759)
+//   euler:  x <- x + d * dt   (model.py:777-783)      else:  out <- d
+// guidance = {g, f, dt} lives in device memory so a captured graph can be replayed with new values.
+// Block = (32 frames) x (32 channels) tile transposed through shared memory (coalesced both ways).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cfg_combine_kernel(const float* __restrict__ proj, const float* __restrict__ guidance, const float* __restrict__ x_in,
+                   float* __restrict__ x_out, int B, int C, int T, int euler) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  const float g = guidance[0], f = guidance[1], dt = guidance[2];
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    float d = 0.f;
+    if (t < T && c < C) {
+      const float df = proj[((size_t)(b)*T + t) * C + c];
+      const float dm = proj[((size_t)(B + b) * T + t) * C + c];
+      const float dn = proj[((size_t)(2 * B + b) * T + t) * C + c];
+      d = dn + g * (dm + f * (df - dm) - dn);
+    }
+    tile[i][tx] = d;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (t < T && c < C) {
+      const size_t off = ((size_t)b * C + c) * T + t;
+      const float d = tile[tx][i];
+      x_out[off] = euler ? x_in[off] + d * dt : d;
+    }
+  }
+}
+
+// token-major [N*T, C] -> channel-first (N, C, T)   (the Rearrange of out_proj, transformerv2.py:429-431)
+__global__ void __launch_bounds__(256)
+tokens_to_channels_kernel(const float* __restrict__ proj, float* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < C) ? proj[((size_t)n * T + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (t < T && c < C) out[((size_t)n * C + c) * T + t] = tile[tx][i];
+  }
+}
+
+}  // namespace after

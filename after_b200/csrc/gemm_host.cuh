@@ -1,0 +1,239 @@
+// Host-side launchers for the tap-GEMMs in gemm.cuh: TMA descriptor creation, tile selection, dispatch between the
+// tcgen05 / SIMT / naive kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <map>
+#include <tuple>
+#include "context.cuh"
+#include "gemm.cuh"
+
+namespace after {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AFTER_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    AFTER_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, -2, "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Weights: 2-D bf16 row-major [rows, cols], box = [box_rows, 64 cols], 128-byte swizzle.
+inline CUtensorMap make_tmap_weight(const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AFTER_REQUIRE(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled(weight) failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
+// Activations: 4-D bf16 (C, P, T, B) with C fastest; box (64, 1, 128, 1).  Frames outside [0, T) are zero-filled
+// by the TMA unit, which is exactly the zero padding of the convolutions.
+inline CUtensorMap make_tmap_act(const void* ptr, int C, int P, int T, int B) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * P * 2, (cuuint64_t)C * P * T * 2};
+  cuuint32_t box[4] = {(cuuint32_t)tc::BK, 1, (cuuint32_t)tc::BM, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AFTER_REQUIRE(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled(activation) failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
+inline int pick_bn(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 32;
+}
+
+// An fp32 weight matrix [N, K] (K = ntaps * Cin, tap-major) with its optional bf16 hi/lo split + TMA maps.
+struct GemmWeight {
+  float* w = nullptr;     // fp32 [N, K]
+  float* bias = nullptr;  // [N] or null
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  CUtensorMap map_hi{}, map_lo{};
+  int N = 0, K = 0, Cin = 0, bn = 0;
+  TapTable taps;
+  bool tc_ok = false;
+};
+
+// A GEMM A-operand buffer: fp32 (SIMT modes) or bf16 hi/lo (tcgen05 modes); the 4-D maps depend on the view
+// (C, P, T, B) and are cached per view.
+struct ActOperand {
+  float* f32 = nullptr;
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  size_t capacity = 0;  // elements
+  struct Maps { CUtensorMap hi, lo; };
+  std::map<std::tuple<int, int, int, int>, Maps> cache;
+  const Maps& maps(int C, int P, int T, int B) {
+    auto key = std::make_tuple(C, P, T, B);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      AFTER_REQUIRE((size_t)C * P * T * B <= capacity, AFTER_EINVAL, "activation view exceeds the operand buffer");
+      Maps m;
+      m.hi = make_tmap_act(hi, C, P, T, B);
+      m.lo = make_tmap_act(lo ? lo : hi, C, P, T, B);
+      it = cache.emplace(key, m).first;
+    }
+    return it->second;
+  }
+};
+
+// fp32 -> bf16 hi/lo split of a whole buffer (weights at finalize time)
+__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __nv_bfloat16 h, l;
+  split_bf16(in[i], h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+// Upload a [N, ntaps*Cin] fp32 weight (+bias) and, in the tensor-core modes, its bf16 split and TMA maps.
+inline void build_gemm_weight(GemmWeight& gw, Arena& arena, const std::vector<float>& w, const float* bias_host, int N,
+                              int Cin, const TapTable& taps, bool tc_mode) {
+  gw.N = N;
+  gw.Cin = Cin;
+  gw.taps = taps;
+  gw.K = taps.ntaps * Cin;
+  AFTER_REQUIRE((size_t)N * gw.K == w.size(), AFTER_ESHAPE, "weight matrix size mismatch");
+  gw.w = arena.upload(w);
+  gw.bias = nullptr;
+  if (bias_host) {
+    std::vector<float> b(bias_host, bias_host + N);
+    gw.bias = arena.upload(b);
+  }
+  gw.bn = pick_bn(N);
+  gw.tc_ok = tc_mode && Cin % tc::BK == 0 && N % 32 == 0 && (taps.n_per_phase == 0 || taps.n_per_phase % gw.bn == 0);
+  if (gw.tc_ok) {
+    const size_t n = w.size();
+    gw.hi = arena.alloc<__nv_bfloat16>(n);
+    gw.lo = arena.alloc<__nv_bfloat16>(n);
+    split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(gw.w, gw.hi, gw.lo, n);
+    AFTER_CUDA_CHECK(cudaGetLastError());
+    gw.map_hi = make_tmap_weight(gw.hi, N, gw.K, gw.bn);
+    gw.map_lo = make_tmap_weight(gw.lo, N, gw.K, gw.bn);
+  }
+}
+
+inline void alloc_operand(ActOperand& op, Arena& arena, size_t elems, bool tc_mode, bool need_f32) {
+  op.capacity = elems;
+  if (tc_mode) {
+    op.hi = arena.alloc<__nv_bfloat16>(elems);
+    op.lo = arena.alloc<__nv_bfloat16>(elems);
+  }
+  if (!tc_mode || need_f32) op.f32 = arena.alloc<float>(elems);
+}
+
+template <int BN>
+inline void launch_tap_gemm_tc_bn(const ActOperand::Maps& am, const GemmWeight& W, const GemmEpi& epi, int B, int T,
+                                  int nprod, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = tc::Smem<BN>::total(nprod > 1 ? 3 : 1);
+  if (!attr_set) {
+    const int mx = std::max(tc::Smem<BN>::total(3), tc::Smem<BN>::total(1));
+    AFTER_CUDA_CHECK(cudaFuncSetAttribute(tc::tap_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set = true;
+  }
+  dim3 grid(W.N / BN, ceil_div(T, tc::BM), B);
+  tc::tap_gemm_tc_kernel<BN><<<grid, tc::NUM_THREADS, smem, st>>>(am.hi, am.lo, W.map_hi, W.map_lo, epi, W.taps, T, W.Cin, nprod);
+  AFTER_CUDA_CHECK(cudaGetLastError());
+}
+
+void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int groups, cudaStream_t st);
+
+// Dispatch.  `precision` is the handle's arithmetic mode.  A: the operand (B, T, P, Cin).  The output is
+// (B, T, N) rows of epi.ldo floats.
+inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, GemmEpi epi, int precision,
+                     cudaStream_t st) {
+  const bool tc_mode = precision != AFTER_PRECISION_FP32_SIMT;
+  epi.bias = W.bias;
+  if (tc_mode && W.tc_ok) {
+    AFTER_REQUIRE(A.hi != nullptr, AFTER_ESTATE, "operand has no bf16 copy");
+    const int nprod = precision == AFTER_PRECISION_BF16 ? 1 : 3;
+    const ActOperand::Maps& am = A.maps(W.Cin, P, T, B);
+    if (W.bn == 128) launch_tap_gemm_tc_bn<128>(am, W, epi, B, T, nprod, st);
+    else if (W.bn == 64) launch_tap_gemm_tc_bn<64>(am, W, epi, B, T, nprod, st);
+    else launch_tap_gemm_tc_bn<32>(am, W, epi, B, T, nprod, st);
+    AFTER_COUNT_LAUNCH();
+    return;
+  }
+  AFTER_REQUIRE(A.f32 != nullptr, AFTER_ESTATE, "operand has no fp32 copy");
+  const bool simt_ok = W.Cin % 16 == 0 && W.N % 4 == 0 && epi.ldo % 4 == 0 &&
+                       (W.taps.n_per_phase == 0 || W.taps.n_per_phase % SG_BN == 0);
+  if (simt_ok) {
+    dim3 grid(ceil_div(W.N, SG_BN), ceil_div(T, SG_BM), B);
+    tap_gemm_simt_kernel<<<grid, 256, 0, st>>>(A.f32, W.w, epi, W.taps, T, P, W.Cin, W.N);
+    AFTER_CUDA_CHECK(cudaGetLastError());
+    AFTER_COUNT_LAUNCH();
+    return;
+  }
+  AFTER_REQUIRE(epi.out_f32 && !epi.out_hi && !epi.rope && epi.ldo == W.N, AFTER_EINVAL,
+                "naive tap-GEMM supports fp32 output only");
+  const size_t total = (size_t)B * T * W.N;
+  tap_gemm_naive_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A.f32, W.w, W.bias, epi.res, epi.out_f32, W.taps,
+                                                                         B, T, P, W.Cin, W.N, epi.gelu);
+  AFTER_CUDA_CHECK(cudaGetLastError());
+  AFTER_COUNT_LAUNCH();
+  if (epi.stats) {
+    const int C = epi.stat_cmod > 0 ? epi.stat_cmod : W.N;
+    gn_stats_launch(epi.out_f32, epi.stats, B, T * (W.N / C), C, epi.stat_groups, st);
+  }
+}
+
+// Unit-test entry: C[M,N] = A[M,K] W[N,K]^T (+bias), all device fp32, through the kernel `precision` selects.
+inline void debug_gemm(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int precision,
+                       cudaStream_t st) {
+  AFTER_REQUIRE(precision >= 0 && precision <= 2, AFTER_EINVAL, "unknown precision");
+  const bool tcm = precision != AFTER_PRECISION_FP32_SIMT;
+  if (tcm) AFTER_REQUIRE(K % 64 == 0 && N % 32 == 0, AFTER_EINVAL, "tcgen05 GEMM needs K % 64 == 0 and N % 32 == 0");
+  else AFTER_REQUIRE(K % 16 == 0 && N % 4 == 0, AFTER_EINVAL, "SIMT GEMM needs K % 16 == 0 and N % 4 == 0");
+  Arena tmp;
+  try {
+    GemmWeight gw;
+    gw.N = N; gw.Cin = K; gw.K = K; gw.bn = pick_bn(N);
+    gw.w = const_cast<float*>(W);
+    gw.bias = const_cast<float*>(bias);
+    ActOperand a;
+    a.capacity = (size_t)M * K;
+    a.f32 = const_cast<float*>(A);
+    if (tcm) {
+      const size_t nw = (size_t)N * K, na = (size_t)M * K;
+      gw.hi = tmp.alloc<__nv_bfloat16>(nw); gw.lo = tmp.alloc<__nv_bfloat16>(nw);
+      a.hi = tmp.alloc<__nv_bfloat16>(na); a.lo = tmp.alloc<__nv_bfloat16>(na);
+      split_bf16_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(W, gw.hi, gw.lo, nw);
+      split_bf16_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, a.hi, a.lo, na);
+      AFTER_CUDA_CHECK(cudaGetLastError());
+      gw.map_hi = make_tmap_weight(gw.hi, N, K, gw.bn);
+      gw.map_lo = make_tmap_weight(gw.lo, N, K, gw.bn);
+      gw.tc_ok = true;
+    }
+    GemmEpi e; e.out_f32 = C; e.ldo = N;
+    tap_gemm(a, 1, M, 1, gw, e, precision, st);
+    AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
+  } catch (...) {
+    cudaStreamSynchronize(st);
+    tmp.release();
+    throw;
+  }
+  tmp.release();
+}
+
+}  // namespace after

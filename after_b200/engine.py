@@ -1,0 +1,283 @@
+"""``Engine``: one libafter_b200 handle on one GPU (weights + workspace), fed from reference
+``state_dict``s.  The classes in ``after_b200.diffusion`` / ``after_b200.autoencoder`` are thin,
+reference-shaped views over an Engine; torch tensors appear only at this boundary (device
+pointers + the current CUDA stream are handed to the C ABI).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .config import AutoEncoderConfig, DenoiserConfig, Encoder1DConfig, ModelConfig
+
+
+def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], max_batch: int, max_steps: int,
+                 seq_len: Optional[int], max_samples: int, use_structure: bool) -> L.AfterConfig:
+    c = L.AfterConfig()
+    c.abi_version = L.ABI_VERSION
+    d: DenoiserConfig = model.denoiser if model is not None else DenoiserConfig()
+    c.n_channels = d.n_channels
+    c.seq_len = seq_len if seq_len is not None else d.seq_len
+    c.embed_dim = d.embed_dim
+    c.cond_dim = d.cond_dim
+    c.noise_embed_dims = d.noise_embed_dims
+    c.n_layers = d.n_layers
+    c.mlp_multiplier = d.mlp_multiplier
+    c.tcond_dim = d.tcond_dim
+    c.local_attention_size = d.local_attention_size
+    c.attention_chunk_size = d.attention_chunk_size
+    c.drop_value = model.drop_value if model is not None else -4.0
+    c.max_batch = max_batch
+    c.max_steps = max_steps
+    if ae is not None:
+        n = len(ae.factors)
+        if n > L.MAX_STAGES:
+            raise ValueError("too many codec stages")
+        c.ae_in_channels = ae.in_channels
+        c.ae_channels = ae.channels
+        c.ae_z_channels = ae.z_channels
+        c.ae_pqmf_bands = ae.pqmf_bands
+        c.ae_n_stages = n
+        for i, m in enumerate(ae.multipliers):
+            c.ae_multipliers[i] = m
+        for i, m in enumerate(ae.decoder_multipliers):
+            c.ae_dec_multipliers[i] = m
+        for i, f in enumerate(ae.factors):
+            c.ae_factors[i] = f
+        for i, dl in enumerate(ae.dilations[:ae.num_blocks]):
+            c.ae_dilations[i] = dl
+        c.ae_num_blocks = ae.num_blocks
+        c.ae_kernel_size = ae.kernel_size
+        c.ae_use_loudness = int(ae.use_loudness)
+        c.ae_max_samples = max_samples
+    se: Optional[Encoder1DConfig] = model.structure_encoder if (model is not None and use_structure) else None
+    if se is not None:
+        if any(r != 1 for r in se.ratios):
+            raise ValueError("structure encoder ratios other than 1 are not supported (no shipped config uses them)")
+        c.se_in_size = se.in_size
+        c.se_n_blocks = len(se.channels)
+        for i, ch in enumerate(se.channels):
+            c.se_channels[i] = ch
+        c.se_kernel_size = se.kernel_size
+        c.se_causal = int(se.causal)
+        c.se_use_tanh = int(se.use_tanh)
+    return c
+
+
+class Engine:
+    """Owns one ``after_handle``.  Not re-entrant: one Engine per (device, caller thread)."""
+
+    def __init__(self,
+                 model: Optional[ModelConfig] = None,
+                 autoencoder: Optional[AutoEncoderConfig] = None,
+                 denoiser_state: Optional[Dict[str, torch.Tensor]] = None,
+                 autoencoder_state: Optional[Dict[str, torch.Tensor]] = None,
+                 structure_state: Optional[Dict[str, torch.Tensor]] = None,
+                 precision: str = "fp32",
+                 device: int = 0,
+                 max_batch: int = 8,
+                 max_steps: int = 50,
+                 seq_len: Optional[int] = None,
+                 max_samples: int = 524288):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        if precision not in L.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(L.PRECISIONS)}")
+        self.precision = precision
+        self.device = torch.device("cuda", device)
+        self.model_cfg = model
+        self.ae_cfg = autoencoder
+        self.cfg = _fill_config(model, autoencoder if autoencoder_state is not None else None, max_batch, max_steps,
+                                seq_len, max_samples, structure_state is not None)
+        L.check(self._lib.after_create(C.byref(self.cfg), device, C.byref(self._h)), None, "after_create")
+        try:
+            if denoiser_state is not None:
+                self._load(L.MODULE_DENOISER, denoiser_state)
+            if autoencoder_state is not None:
+                self._load(L.MODULE_AUTOENCODER, autoencoder_state)
+            if structure_state is not None:
+                self._load(L.MODULE_STRUCTURE_ENCODER, structure_state)
+            if denoiser_state is not None or autoencoder_state is not None or structure_state is not None:
+                L.check(self._lib.after_finalize_weights(self._h, L.PRECISIONS[precision]), self._h,
+                        "after_finalize_weights")
+        except Exception:
+            self.close()
+            raise
+        self.has_denoiser = denoiser_state is not None
+        self.has_codec = autoencoder_state is not None
+        self.has_structure = structure_state is not None
+
+    # ------------------------------------------------------------------ plumbing
+    def _load(self, module: int, sd: Dict[str, torch.Tensor]):
+        for key, t in sd.items():
+            t = t.detach().cpu().contiguous()
+            if t.dtype == torch.float32:
+                dt = L.DTYPE_F32
+            elif t.dtype == torch.float64:
+                dt = L.DTYPE_F64
+            elif t.dtype == torch.int64:
+                dt = L.DTYPE_I64
+            else:
+                t = t.float()
+                dt = L.DTYPE_F32
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            L.check(
+                self._lib.after_load_tensor(self._h, module, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt),
+                self._h, f"after_load_tensor({key})")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.after_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, this engine lives on {self.device} (no implicit copies, no CPU path)")
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.after_launch_count(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.after_device_bytes(self._h))
+
+    @property
+    def ae_ratio(self) -> int:
+        return int(self._lib.after_ae_ratio(self._h))
+
+    # ------------------------------------------------------------------ compute entry points
+    def denoiser_forward(self, x, time, cond, time_cond):
+        x = self._dev(x, "x")
+        N, _, T = x.shape
+        time = self._dev(time, "time")
+        if time.dim() > 1:
+            time = time.reshape(N, -1)[:, 0]  # only [..., 0] is read (transformerv2.py:524-528)
+        time = time.contiguous()
+        cond = self._dev(cond, "cond")
+        time_cond = self._dev(time_cond, "time_cond")
+        self._check_cond(cond, time_cond, N, T)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_denoiser_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
+                                                 out.data_ptr(), N, T, self._stream()), self._h, "after_denoiser_forward")
+        return out
+
+    def _check_cond(self, cond, time_cond, B, T):
+        if tuple(cond.shape) != (B, self.cfg.cond_dim):
+            raise ValueError(f"cond must be ({B}, {self.cfg.cond_dim}), got {tuple(cond.shape)}")
+        if tuple(time_cond.shape) != (B, self.cfg.tcond_dim, T):
+            raise ValueError(f"time_cond must be ({B}, {self.cfg.tcond_dim}, {T}), got {tuple(time_cond.shape)}")
+
+    def model_forward(self, x, time, cond, time_cond, guidance_timbre, guidance_structure, cfg_variant=L.CFG_AUDIO,
+                      clamp=0.01):
+        x = self._dev(x, "x")
+        B, _, T = x.shape
+        time = self._dev(time, "time").reshape(B, -1)[:, 0].contiguous()
+        cond = self._dev(cond, "cond")
+        time_cond = self._dev(time_cond, "time_cond")
+        self._check_cond(cond, time_cond, B, T)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_model_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
+                                              out.data_ptr(), B, T, float(guidance_timbre), float(guidance_structure),
+                                              int(cfg_variant), float(clamp), self._stream()), self._h, "after_model_forward")
+        return out
+
+    def sample(self, x0, cond, time_cond, nb_steps, guidance_timbre=1.0, guidance_structure=1.0, cfg_variant=L.CFG_AUDIO,
+               clamp=0.01):
+        x0 = self._dev(x0, "x0")
+        B, _, T = x0.shape
+        cond = self._dev(cond, "cond")
+        time_cond = self._dev(time_cond, "time_cond")
+        self._check_cond(cond, time_cond, B, T)
+        out = torch.empty_like(x0)
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_sample(self._h, x0.data_ptr(), cond.data_ptr(), time_cond.data_ptr(), out.data_ptr(), B, T,
+                                       int(nb_steps), float(guidance_timbre), float(guidance_structure), int(cfg_variant),
+                                       float(clamp), self._stream()), self._h, "after_sample")
+        return out
+
+    def sample_host(self, x0, cond, time_cond, out, nb_steps, guidance_timbre=1.0, guidance_structure=1.0,
+                    cfg_variant=L.CFG_AUDIO, clamp=0.01):
+        """HOST tensors in, HOST tensor out (``out`` is filled and returned); H2D/D2H happen inside the call."""
+        for name, t in (("x0", x0), ("cond", cond), ("time_cond", time_cond), ("out", out)):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous fp32 CPU tensor")
+        B, _, T = x0.shape
+        self._check_cond(cond, time_cond, B, T)
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_sample_host(self._h, x0.data_ptr(), cond.data_ptr(), time_cond.data_ptr(), out.data_ptr(), B, T,
+                                            int(nb_steps), float(guidance_timbre), float(guidance_structure),
+                                            int(cfg_variant), float(clamp), self._stream()), self._h, "after_sample_host")
+        return out
+
+    def ae_encode(self, audio):
+        audio = self._dev(audio, "audio")
+        if audio.dim() != 3 or audio.shape[1] != 1:
+            raise ValueError("audio must be (B, 1, samples)")
+        B, _, S = audio.shape
+        r = self.ae_ratio
+        if r == 0:
+            raise RuntimeError("this engine has no codec")
+        if S % r:
+            raise ValueError(f"samples ({S}) must be a multiple of the codec ratio ({r})")
+        z = torch.empty(B, self.cfg.ae_z_channels, S // r, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_ae_encode(self._h, audio.data_ptr(), z.data_ptr(), B, S, self._stream()), self._h,
+                    "after_ae_encode")
+        return z
+
+    def ae_decode(self, z):
+        z = self._dev(z, "z")
+        B, Cz, T = z.shape
+        if Cz != self.cfg.ae_z_channels:
+            raise ValueError(f"z must have {self.cfg.ae_z_channels} channels")
+        audio = torch.empty(B, 1, T * self.ae_ratio, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_ae_decode(self._h, z.data_ptr(), audio.data_ptr(), B, T, self._stream()), self._h,
+                    "after_ae_decode")
+        return audio
+
+    def structure_encode(self, z):
+        z = self._dev(z, "z")
+        B, Cin, T = z.shape
+        out = torch.empty(B, self.cfg.se_channels[self.cfg.se_n_blocks - 1], T, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_structure_encode(self._h, z.data_ptr(), out.data_ptr(), B, T, self._stream()), self._h,
+                    "after_structure_encode")
+        return out
+
+    def debug_gemm(self, A, W, bias=None, precision="fp32"):
+        A = self._dev(A, "A")
+        W = self._dev(W, "W")
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, device=self.device, dtype=torch.float32)
+        b = self._dev(bias, "bias").data_ptr() if bias is not None else None
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_debug_gemm(self._h, A.data_ptr(), W.data_ptr(), b, out.data_ptr(), M, N, K,
+                                           L.PRECISIONS[precision], self._stream()), self._h, "after_debug_gemm")
+        return out

@@ -1,0 +1,181 @@
+/*
+ * after_b200.h -- C ABI of libafter_b200.so, the B200 (sm_100a) implementation of AFTER's
+ * latent-sampling hot path.
+ *
+ * The reference (acids-ircam/AFTER) is pure Python/PyTorch and has no FFI of its own; each entry
+ * point below names the reference *Python* call it replaces (file:line under /root/reference) --
+ * that is the interface a binding (ctypes here, a TORCH_LIBRARY op or an nn_tilde backend
+ * elsewhere) forwards to.  See INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - plain C types only; tensors are raw pointers to contiguous fp32 (unless stated) with the
+ *     reference's layouts: audio (B,1,S), latents (B,C,T) channel-first, cond (B,zt),
+ *     time_cond (B,zs,T).
+ *   - "dev" pointers are device pointers on the handle's GPU, "host" pointers are host memory.
+ *   - every function returns 0 on success, a negative AFTER_E* code on failure;
+ *     after_last_error(h) returns a human-readable message for the last failure on that handle
+ *     (after_last_error(NULL): last failure of a call that had no handle).
+ *   - a handle is NOT re-entrant: one handle per (device, stream); the caller serialises.
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream` (NULL = legacy default
+ *     stream); functions do not synchronise unless stated.
+ *   - the library owns its weight copies and workspace; it never retains or frees caller
+ *     pointers.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef AFTER_B200_H_
+#define AFTER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFTER_B200_ABI_VERSION 1
+
+/* error codes */
+#define AFTER_OK 0
+#define AFTER_IGNORED 1          /* after_load_tensor: key is not a parameter this path uses */
+#define AFTER_EINVAL (-1)        /* bad argument / unsupported configuration */
+#define AFTER_ECUDA (-2)         /* CUDA runtime / driver error */
+#define AFTER_ESTATE (-3)        /* call order violated (e.g. compute before finalize) */
+#define AFTER_EMISSING (-4)      /* finalize: a required tensor was never loaded */
+#define AFTER_ESHAPE (-5)        /* tensor shape does not match the configuration */
+#define AFTER_ENOMEM (-6)
+
+/* arithmetic modes (after_finalize_weights) */
+#define AFTER_PRECISION_FP32 0   /* tcgen05 bf16x3 split products, fp32 accumulate: fp32-accurate */
+#define AFTER_PRECISION_BF16 1   /* tcgen05 single bf16 product, fp32 accumulate */
+#define AFTER_PRECISION_FP32_SIMT 2 /* fp32 FFMA everywhere (validation path, no tensor cores) */
+
+/* tensor dtypes accepted by after_load_tensor */
+#define AFTER_DTYPE_F32 0
+#define AFTER_DTYPE_F64 1
+#define AFTER_DTYPE_I64 2
+
+/* which sub-model a tensor belongs to (state-dict key namespaces are per module in the reference) */
+#define AFTER_MODULE_DENOISER 0          /* RectifiedFlow.net        : DenoiserV2 state_dict   */
+#define AFTER_MODULE_AUTOENCODER 1       /* emb_model                : AutoEncoder state_dict  */
+#define AFTER_MODULE_STRUCTURE_ENCODER 2 /* RectifiedFlow.encoder_time: Encoder1D state_dict   */
+#define AFTER_MODULE_TIMBRE_ENCODER 3    /* RectifiedFlow.encoder    : ECAPATDNN state_dict    */
+
+/* classifier-free-guidance row layouts */
+#define AFTER_CFG_AUDIO 0 /* (cond,tc)/(drop,tc)/(drop,drop), f = g_t/max(g_s,clamp)  model.py:730-759 */
+#define AFTER_CFG_MIDI 1  /* (cond,tc)/(cond,drop)/(drop,drop), f = g_s/max(g_t,clamp) export_midi.py:322-360 */
+
+#define AFTER_MAX_STAGES 8
+
+/* Hyper-parameters; mirrors the gin bindings of the reference (base.gin:65-78, baseAE.gin:35-52).
+ * A field set to 0 in the optional sub-models disables that sub-model. */
+typedef struct after_config {
+  int32_t abi_version; /* must be AFTER_B200_ABI_VERSION */
+  /* --- DenoiserV2 (transformerv2.py:463-476) --- */
+  int32_t n_channels;           /* latent channels (64) */
+  int32_t seq_len;              /* maximum frames per sequence the workspace is sized for (256) */
+  int32_t embed_dim;            /* 256 | 512 */
+  int32_t cond_dim;             /* timbre dims (6) */
+  int32_t noise_embed_dims;     /* fourier features (64) */
+  int32_t n_layers;             /* 6 */
+  int32_t mlp_multiplier;       /* 3 */
+  int32_t tcond_dim;            /* structure dims (12, midi 128) */
+  int32_t local_attention_size; /* 8 (midi 16) */
+  int32_t attention_chunk_size; /* 4 */
+  float drop_value;             /* -4.0 (base.gin:88) */
+  int32_t max_batch;            /* largest B (streams) a call may pass; CFG rows = 3B */
+  int32_t max_steps;            /* largest nb_steps for after_sample */
+  /* --- AutoEncoder (SimpleNetsStream.py:834-849); ae_channels == 0 disables the codec --- */
+  int32_t ae_in_channels;  /* 16 */
+  int32_t ae_channels;     /* 64 */
+  int32_t ae_z_channels;   /* 64 */
+  int32_t ae_pqmf_bands;   /* 16 */
+  int32_t ae_n_stages;     /* len(factors) */
+  int32_t ae_multipliers[AFTER_MAX_STAGES + 1]; /* encoder multipliers */
+  int32_t ae_dec_multipliers[AFTER_MAX_STAGES + 1]; /* int(m*decoder_ratio) of reversed multipliers */
+  int32_t ae_factors[AFTER_MAX_STAGES];
+  int32_t ae_dilations[AFTER_MAX_STAGES]; /* first ae_num_blocks entries used */
+  int32_t ae_num_blocks;   /* 3 */
+  int32_t ae_kernel_size;  /* 3 */
+  int32_t ae_use_loudness; /* 1 */
+  int64_t ae_max_samples;  /* longest audio (samples) per stream the codec workspace is sized for */
+  /* --- Encoder1D structure encoder (encoder.py:116-237); se_n_blocks == 0 disables --- */
+  int32_t se_in_size;
+  int32_t se_n_blocks;                     /* len(channels) */
+  int32_t se_channels[AFTER_MAX_STAGES];
+  int32_t se_kernel_size;                  /* 5 */
+  int32_t se_causal;                       /* 1: convs.get_padding.mode = 'causal' (base.gin:55) */
+  int32_t se_use_tanh;
+} after_config;
+
+typedef struct after_ctx* after_handle;
+
+/* Library / device discovery (no handle needed). */
+int after_abi_version(void);
+const char* after_build_info(void); /* arch, compiler, build flags */
+int after_device_count(void);
+
+/* Create a handle on CUDA device `device`.  Replaces constructing the reference modules
+ * (RectifiedFlow(net=DenoiserV2(...), ...) model.py:20-50; AutoEncoder(...) SimpleNetsStream.py:834). */
+int after_create(const after_config* cfg, int device, after_handle* out);
+int after_destroy(after_handle h);
+const char* after_last_error(after_handle h);
+
+/* Feed one entry of a reference state_dict (torch.nn.Module.load_state_dict, model.py:221-247;
+ * keys as listed in SURVEY.md appendix A.4).  `data` is HOST memory, C-contiguous.  Weight-norm
+ * pairs (weight_g / weight_v), eval-mode BatchNorm statistics and GroupNorm affines are folded
+ * inside the library at finalize.  Returns AFTER_IGNORED for keys the path does not need
+ * (caches, position tables). */
+int after_load_tensor(after_handle h, int module, const char* key, const void* data,
+                      const int64_t* shape, int ndim, int dtype);
+
+/* Fold / transpose / split the loaded weights, upload them, build TMA descriptors, allocate the
+ * workspace.  Must be called once after the last after_load_tensor and before any compute call. */
+int after_finalize_weights(after_handle h, int precision);
+
+/* DenoiserV2.forward (transformerv2.py:517-543): out = net(x, time, cond, time_cond).
+ * x, out: dev (N,C,T); time: dev (N,) ; cond: dev (N,zt); time_cond: dev (N,zs,T).  N <= 3*max_batch. */
+int after_denoiser_forward(after_handle h, const float* x, const float* time, const float* cond,
+                           const float* time_cond, float* out, int N, int T, void* stream);
+
+/* RectifiedFlow.model_forward (model.py:721-761): one CFG-combined velocity evaluation.
+ * x, out: dev (B,C,T); time: dev (B,); cond dev (B,zt); time_cond dev (B,zs,T). */
+int after_model_forward(after_handle h, const float* x, const float* time, const float* cond,
+                        const float* time_cond, float* out, int B, int T, float guidance_timbre,
+                        float guidance_structure, int cfg_variant, float clamp, void* stream);
+
+/* RectifiedFlow.sample (model.py:763-785): nb_steps Euler steps from x0.  x0,out dev (B,C,T). */
+int after_sample(after_handle h, const float* x0, const float* cond, const float* time_cond,
+                 float* out, int B, int T, int nb_steps, float guidance_timbre,
+                 float guidance_structure, int cfg_variant, float clamp, void* stream);
+
+/* Same as after_sample with HOST buffers (pageable or pinned): H2D of the inputs, the loop, D2H of
+ * the result, and a stream synchronise before returning. */
+int after_sample_host(after_handle h, const float* x0, const float* cond, const float* time_cond,
+                      float* out, int B, int T, int nb_steps, float guidance_timbre,
+                      float guidance_structure, int cfg_variant, float clamp, void* stream);
+
+/* AutoEncoder.encode (SimpleNetsStream.py:918-941; z only, as export_autoencoder.py:251-258):
+ * audio dev (B,1,S) -> z dev (B,Z,S/ratio).  S must be a multiple of the codec ratio. */
+int after_ae_encode(after_handle h, const float* audio, float* z, int B, int64_t samples, void* stream);
+
+/* AutoEncoder.decode (SimpleNetsStream.py:943-954): z dev (B,Z,T) -> audio dev (B,1,T*ratio). */
+int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, void* stream);
+
+/* Encoder1D.forward (encoder.py:273-298): z dev (B,C,T) -> time_cond dev (B,zs,T). */
+int after_structure_encode(after_handle h, const float* z, float* time_cond, int B, int T, void* stream);
+
+/* Introspection for benchmarks: kernels launched by this handle since creation, bytes of device
+ * memory held, codec ratio (samples per latent frame). */
+int64_t after_launch_count(after_handle h);
+int64_t after_device_bytes(after_handle h);
+int after_ae_ratio(after_handle h);
+
+/* Unit-level entry point used by the parity tests of the tensor-core GEMM:
+ * C[M,N] = A[M,K] * W[N,K]^T (+bias[N]) in the given precision; all dev fp32. */
+int after_debug_gemm(after_handle h, const float* A, const float* W, const float* bias, float* C,
+                     int M, int N, int K, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFTER_B200_H_ */
