@@ -1,19 +1,628 @@
-// STUB (replaced below in this round): codec + structure encoder.
+// AutoEncoder.encode / decode (SimpleNetsStream.py:918-954) and Encoder1D.forward (encoder.py:273-298) on one B200.
+//
+// Data layout: every activation is frame-major fp32 (B, T, C) in HBM; a convolution is
+//     act_operand_kernel  : x -> act(norm(x)) written as the GEMM A-operand (bf16 hi/lo for tcgen05, fp32 otherwise)
+//     tap-GEMM            : operand x folded weights -> +bias (+residual) -> fp32 out, and the GroupNorm
+//                           sum / sum-of-squares of the result for the next layer's norm (epilogue atomics)
+// so each activation is written once and read twice (operand pass + residual), never re-read for statistics.
+// Weight-norm (g * v / ||v||, SimpleNetsStream.py:84-92) and eval-mode BatchNorm are folded at load.
+// Strided convs read the input as (B, T/f, f, C) phases; transposed convs write (B, T, f*C) = (B, T*f, C).
 #pragma once
+#include <cmath>
+#include "codec_kernels.cuh"
 #include "context.cuh"
+#include "denoiser_kernels.cuh"
 #include "gemm_host.cuh"
+
 namespace after {
-inline void gn_stats_launch(const float*, double*, int, int, int, int, cudaStream_t) {
-  throw Error(AFTER_ESTATE, "not implemented");
+
+inline void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int groups, cudaStream_t st) {
+  dim3 grid(ceil_div(T, 256), B);
+  gn_stats_kernel<<<grid, 256, 0, st>>>(x, stats, T, C, groups);
+  AFTER_CUDA_CHECK(cudaGetLastError());
+  AFTER_COUNT_LAUNCH();
 }
-struct Codec {
-  void finalize(const after_config&, const TensorMap&, int, Arena*) { throw Error(AFTER_ESTATE, "codec not implemented"); }
-  void encode(const float*, float*, int, int64_t, cudaStream_t) { throw Error(AFTER_ESTATE, "codec not implemented"); }
-  void decode(const float*, float*, int, int, cudaStream_t) { throw Error(AFTER_ESTATE, "codec not implemented"); }
-  void destroy() {}
+
+// Replayable CUDA graphs keyed by the call signature.
+struct GraphCache {
+  struct Entry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t kernels = 0;
+  };
+  std::map<std::vector<int>, Entry> graphs;
+  bool enabled = true;
+  void init() {
+    const char* ng = getenv("AFTER_NO_GRAPH");
+    enabled = !(ng && ng[0] == '1');
+  }
+  template <typename F>
+  void run(const std::vector<int>& key, cudaStream_t st, F&& body) {
+    if (!enabled) {
+      body();
+      return;
+    }
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      Entry ge;
+      cudaGraph_t graph = nullptr;
+      const int64_t before = g_launches.load();
+      AFTER_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        body();
+      } catch (...) {
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      AFTER_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+      ge.kernels = g_launches.load() - before;
+      g_launches.fetch_sub(ge.kernels);  // capture did not execute anything
+      AFTER_CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = graphs.emplace(key, ge).first;
+    }
+    AFTER_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
+    g_launches.fetch_add(it->second.kernels);
+  }
+  void destroy() {
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
 };
-struct StructureEncoder {
-  void finalize(const after_config&, const TensorMap&, int, Arena*) { throw Error(AFTER_ESTATE, "not implemented"); }
-  void forward(const float*, float*, int, int, cudaStream_t) { throw Error(AFTER_ESTATE, "not implemented"); }
+
+// ------------------------------------------------------------------------------------------- tap tables
+// cached_conv.get_padding semantics: centered -> left = (p-1)/2, causal -> left = p-1,
+// with p = (k-1)*dilation + 1.
+inline TapTable conv_taps(int k, int dilation, bool causal) {
+  AFTER_REQUIRE(k >= 1 && k <= MAX_TAPS, AFTER_EINVAL, "conv kernel size not supported");
+  TapTable t;
+  t.ntaps = k;
+  const int p = (k - 1) * dilation + 1;
+  const int left = k == 1 ? 0 : (causal ? p / 2 + (p - 1) / 2 : (p - 1) / 2);
+  for (int i = 0; i < k; ++i) {
+    t.phase[0][i] = 0;
+    t.shift[0][i] = (int16_t)(i * dilation - left);
+  }
+  return t;
+}
+// Downsample1d: conv k = 2f, stride f, padding get_padding(2f) = (f-1, f)   (SimpleNetsStream.py:32-48)
+inline TapTable strided_taps(int f) {
+  AFTER_REQUIRE(2 * f <= MAX_TAPS, AFTER_EINVAL, "downsampling factor too large");
+  TapTable t;
+  t.ntaps = 2 * f;
+  for (int k = 0; k < 2 * f; ++k) {
+    const int j = k - (f - 1);
+    const int ph = ((j % f) + f) % f;
+    t.phase[0][k] = (int8_t)ph;
+    t.shift[0][k] = (int16_t)((j - ph) / f);
+  }
+  return t;
+}
+// Upsample1d: ConvTranspose1d k = 2f, stride f, padding f/2 (SimpleNetsStream.py:51-70).  Output phase r of frame
+// t gets taps k0 = (r + pad) mod f from input frame t + (r + pad) / f and k0 + f from the frame before it.
+inline TapTable transposed_taps(int f, int cout, int* kidx /*[f][2]*/) {
+  AFTER_REQUIRE(f <= MAX_PHASES, AFTER_EINVAL, "upsampling factor too large");
+  TapTable t;
+  t.ntaps = 2;
+  t.n_per_phase = cout;
+  const int pad = f / 2;
+  for (int r = 0; r < f; ++r) {
+    const int k0 = (r + pad) % f, s = (r + pad) / f;
+    t.phase[r][0] = 0; t.shift[r][0] = (int16_t)s;       kidx[r * 2 + 0] = k0;
+    t.phase[r][1] = 0; t.shift[r][1] = (int16_t)(s - 1); kidx[r * 2 + 1] = k0 + f;
+  }
+  return t;
+}
+
+struct ConvLayer {
+  GemmWeight w;
+  int cin = 0, cout = 0;
+  int in_phases = 1;   // input frames per GEMM row (stride of a strided conv)
+  int out_phases = 1;  // output frames per GEMM row (stride of a transposed conv)
 };
+
+struct NormAct {
+  int C = 0, groups = 1;
+  int norm = NORM_NONE, act = ACT_NONE;
+  float *gamma = nullptr, *beta = nullptr, *alpha = nullptr, *inv_beta = nullptr;  // GroupNorm affine, Snake
+  float *mu = nullptr, *rs = nullptr, *be = nullptr;                              // folded BatchNorm
+};
+
+struct ResBlock {
+  NormAct a1, a2;
+  ConvLayer c1, c2, skip;
+  bool has_skip = false;
+};
+
+// Shared machinery of the two conv nets.
+struct ConvNet {
+  Arena* arena = nullptr;
+  int precision = 0;
+  const TensorMap* sd = nullptr;
+  bool tc_mode() const { return precision != AFTER_PRECISION_FP32_SIMT; }
+  int nprod() const { return precision == AFTER_PRECISION_BF16 ? 1 : 3; }
+
+  // workspace
+  float* buf[3] = {nullptr, nullptr, nullptr};
+  ActOperand op;
+  double* stats = nullptr;
+  int stat_slots = 0, stat_next = 0;
+  size_t slot_doubles = 0;
+  size_t buf_elems = 0;
+  int maxB = 0;
+  GraphCache graphs;
+
+  const HostTensor& get(const std::string& key) const {
+    auto it = sd->find(key);
+    if (it == sd->end()) throw Error(AFTER_EMISSING, "missing tensor '" + key + "'");
+    return it->second;
+  }
+  bool has(const std::string& key) const { return sd->find(key) != sd->end(); }
+
+  std::vector<float> folded(const std::string& prefix) const {
+    return fold_weight_norm(get(prefix + ".weight_v"), get(prefix + ".weight_g"));
+  }
+
+  // Conv1d weight (cout, cin, k) -> [cout][k*cin + ci]
+  void make_conv(ConvLayer& L, const std::string& prefix, int cin, int cout, int k, const TapTable& taps, int in_phases) {
+    const HostTensor& v = get(prefix + ".weight_v");
+    AFTER_REQUIRE(v.shape.size() == 3 && v.shape[0] == cout && v.shape[1] == cin && v.shape[2] == k, AFTER_ESHAPE,
+                  "tensor '" + prefix + ".weight_v' has an unexpected shape");
+    const std::vector<float> w = folded(prefix);
+    std::vector<float> m((size_t)cout * k * cin);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int kk = 0; kk < k; ++kk) m[((size_t)o * k + kk) * cin + c] = w[((size_t)o * cin + c) * k + kk];
+    const HostTensor& b = get(prefix + ".bias");
+    AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
+    build_gemm_weight(L.w, *arena, m, b.data.data(), cout, cin, taps, tc_mode());
+    L.cin = cin; L.cout = cout; L.in_phases = in_phases; L.out_phases = 1;
+  }
+
+  // ConvTranspose1d weight (cin, cout, 2f) -> [r*cout + co][tap*cin + ci]
+  void make_conv_transposed(ConvLayer& L, const std::string& prefix, int cin, int cout, int f) {
+    const HostTensor& v = get(prefix + ".weight_v");
+    AFTER_REQUIRE(v.shape.size() == 3 && v.shape[0] == cin && v.shape[1] == cout && v.shape[2] == 2 * f, AFTER_ESHAPE,
+                  "tensor '" + prefix + ".weight_v' has an unexpected shape");
+    const std::vector<float> w = folded(prefix);  // norm per input channel (dim 0)
+    int kidx[MAX_PHASES * 2];
+    TapTable taps = transposed_taps(f, cout, kidx);
+    const int k = 2 * f;
+    std::vector<float> m((size_t)f * cout * 2 * cin);
+    for (int r = 0; r < f; ++r)
+      for (int o = 0; o < cout; ++o)
+        for (int tap = 0; tap < 2; ++tap)
+          for (int c = 0; c < cin; ++c)
+            m[(((size_t)r * cout + o) * 2 + tap) * cin + c] = w[((size_t)c * cout + o) * k + kidx[r * 2 + tap]];
+    const HostTensor& b = get(prefix + ".bias");
+    AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
+    std::vector<float> bias((size_t)f * cout);
+    for (int r = 0; r < f; ++r) std::copy(b.data.begin(), b.data.end(), bias.begin() + (size_t)r * cout);
+    build_gemm_weight(L.w, *arena, m, bias.data(), f * cout, cin, taps, tc_mode());
+    L.cin = cin; L.cout = cout; L.in_phases = 1; L.out_phases = f;
+  }
+
+  void make_snake(NormAct& a, const std::string& prefix, int C) {
+    const HostTensor& al = get(prefix + ".alpha");
+    const HostTensor& be = get(prefix + ".beta");
+    AFTER_REQUIRE(al.numel() == C && be.numel() == C, AFTER_ESHAPE, "tensor '" + prefix + ".alpha' has an unexpected shape");
+    std::vector<float> ib(C);
+    for (int c = 0; c < C; ++c) ib[c] = 1.0f / (be.data[c] + 1e-9f);
+    a.C = C;
+    a.act = ACT_SNAKE;
+    a.alpha = arena->upload(al.data);
+    a.inv_beta = arena->upload(ib);
+  }
+  // ConvBlock1d prologue: CachedGroupNorm(min(C, groups)) -> SnakeBeta   (SimpleNetsStream.py:150-194)
+  void make_gn_snake(NormAct& a, const std::string& prefix, int C, int groups) {
+    make_snake(a, prefix + ".net.1", C);
+    a.norm = NORM_GROUP;
+    a.groups = std::min(C, groups);
+    AFTER_REQUIRE(C % a.groups == 0, AFTER_EINVAL, "GroupNorm channels not divisible by groups");
+    const HostTensor& g = get(prefix + ".net.0.gn.weight");
+    const HostTensor& b = get(prefix + ".net.0.gn.bias");
+    AFTER_REQUIRE(g.numel() == C && b.numel() == C, AFTER_ESHAPE, "tensor '" + prefix + ".net.0.gn.weight' has an unexpected shape");
+    a.gamma = arena->upload(g.data);
+    a.beta = arena->upload(b.data);
+  }
+  // eval-mode BatchNorm1d -> SiLU   (encoder.py:39-48)
+  void make_bn_silu(NormAct& a, const std::string& prefix, int C) {
+    const HostTensor& w = get(prefix + ".weight");
+    const HostTensor& b = get(prefix + ".bias");
+    const HostTensor& rm = get(prefix + ".running_mean");
+    const HostTensor& rv = get(prefix + ".running_var");
+    AFTER_REQUIRE(w.numel() == C && b.numel() == C && rm.numel() == C && rv.numel() == C, AFTER_ESHAPE,
+                  "tensor '" + prefix + ".weight' has an unexpected shape");
+    std::vector<float> rs(C);
+    for (int c = 0; c < C; ++c) rs[c] = w.data[c] / std::sqrt(rv.data[c] + 1e-5f);
+    a.C = C;
+    a.norm = NORM_AFFINE;
+    a.act = ACT_SILU;
+    a.mu = arena->upload(rm.data);
+    a.rs = arena->upload(rs);
+    a.be = arena->upload(b.data);
+  }
+
+  void alloc_workspace(size_t elems_per_stream, int max_batch, int slots) {
+    maxB = max_batch;
+    buf_elems = elems_per_stream * (size_t)max_batch;
+    for (auto& b : buf) b = arena->alloc<float>(buf_elems);
+    alloc_operand(op, *arena, buf_elems, tc_mode(), true);
+    stat_slots = slots;
+    slot_doubles = (size_t)max_batch * 8 * 2;
+    stats = arena->alloc<double>(slot_doubles * slots);
+    graphs.init();
+  }
+
+  // ---- run-time helpers -------------------------------------------------------------------
+  double* new_slot() {
+    AFTER_REQUIRE(stat_next < stat_slots, AFTER_ESTATE, "statistics arena exhausted");
+    return stats + slot_doubles * (stat_next++);
+  }
+  void begin(cudaStream_t st) {
+    stat_next = 0;
+    AFTER_CUDA_CHECK(cudaMemsetAsync(stats, 0, slot_doubles * stat_slots * sizeof(double), st));
+  }
+
+  // operand <- act(norm(x)) in the format the consuming conv wants
+  void produce(const float* x, const NormAct& a, const double* xstats, const ConvLayer& consumer, int B, int T, int C,
+               cudaStream_t st) {
+    AFTER_REQUIRE((size_t)B * T * C <= buf_elems, AFTER_EINVAL, "activation exceeds the codec workspace");
+    ActParams p;
+    p.norm = a.norm; p.act = a.act;
+    p.stats = xstats; p.groups = a.groups; p.gamma = a.gamma; p.beta = a.beta;
+    p.mu = a.mu; p.rs = a.rs; p.be = a.be; p.alpha = a.alpha; p.inv_beta = a.inv_beta;
+    if (a.norm == NORM_GROUP) AFTER_REQUIRE(xstats != nullptr, AFTER_ESTATE, "GroupNorm input has no statistics");
+    OperandOut o;
+    if (tc_mode() && consumer.w.tc_ok) { o.hi = op.hi; o.lo = nprod() > 1 ? op.lo : nullptr; }
+    else o.f32 = op.f32;
+    const int fpb = std::max(1, 16384 / C);
+    dim3 grid(ceil_div(T, fpb), B);
+    const size_t smem = (size_t)5 * C * sizeof(float);
+    if (C % 4 == 0) act_operand_kernel<4><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
+    else act_operand_kernel<1><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
+    AFTER_CUDA_CHECK(cudaGetLastError());
+    AFTER_COUNT_LAUNCH();
+  }
+
+  // out (B, T_rows * out_phases, cout) <- conv(operand) + bias (+ res); optional statistics of the result.
+  // T_rows = GEMM rows per stream = input frames / in_phases.
+  void conv(const ConvLayer& L, int B, int T_rows, float* out, const float* res, double* out_stats, int stat_groups,
+            cudaStream_t st) {
+    GemmEpi e;
+    e.out_f32 = out;
+    e.ldo = L.w.N;
+    e.res = res;
+    if (out_stats) {
+      e.stats = out_stats;
+      e.stat_groups = stat_groups;
+      e.stat_cpg = L.cout / stat_groups;
+      e.stat_cmod = L.out_phases > 1 ? L.cout : 0;
+    }
+    tap_gemm(op, B, T_rows, L.in_phases, L.w, e, precision, st);
+  }
+
+  // ResnetBlock1d: block2(block1(x)) + skip(x)   (SimpleNetsStream.py:197-254).  x -> out (distinct buffers), y1 scratch.
+  void res_block(const ResBlock& r, const float* x, const double* xstats, float* y1, float* out, double* out_stats,
+                 int out_groups, int B, int T, cudaStream_t st) {
+    const float* res = x;
+    if (r.has_skip) {
+      NormAct ident;
+      produce(x, ident, nullptr, r.skip, B, T, r.skip.cin, st);
+      conv(r.skip, B, T, out, nullptr, nullptr, 1, st);
+      res = out;
+    }
+    double* s1 = new_slot();
+    produce(x, r.a1, xstats, r.c1, B, T, r.c1.cin, st);
+    conv(r.c1, B, T, y1, nullptr, s1, r.a2.groups, st);
+    produce(y1, r.a2, s1, r.c2, B, T, r.c2.cin, st);
+    conv(r.c2, B, T, out, res, out_stats, out_groups, st);
+  }
+
+  void make_res(ResBlock& r, const std::string& prefix, int cin, int cout, int k, int dilation, int groups, bool causal) {
+    make_gn_snake(r.a1, prefix + ".net.branches.0.0", cin, groups);
+    make_conv(r.c1, prefix + ".net.branches.0.0.net.2", cin, cout, k, conv_taps(k, dilation, causal), 1);
+    make_gn_snake(r.a2, prefix + ".net.branches.0.1", cout, 8);
+    make_conv(r.c2, prefix + ".net.branches.0.1.net.2", cout, cout, 1, conv_taps(1, 1, false), 1);
+    r.has_skip = has(prefix + ".net.branches.1.weight_v");
+    if (r.has_skip) make_conv(r.skip, prefix + ".net.branches.1", cin, cout, 1, conv_taps(1, 1, false), 1);
+    else AFTER_REQUIRE(cin == cout, AFTER_EMISSING, "missing skip convolution '" + prefix + ".net.branches.1'");
+  }
+};
+
+// ===========================================================================================
+struct Codec : ConvNet {
+  after_config cfg{};
+  int M = 16, n_stages = 0, nb = 0, ratio = 1;
+  std::vector<int> ech, dch;
+  // encoder
+  ResBlock to_in;
+  struct Down { std::vector<ResBlock> res; NormAct snake; ConvLayer conv; int f; };
+  std::vector<Down> downs;
+  NormAct enc_out_snake; ConvLayer enc_out;
+  // decoder
+  ConvLayer dec_in;
+  struct Up { NormAct snake; ConvLayer conv; std::vector<ResBlock> res; int f; };
+  std::vector<Up> ups;
+  NormAct out_a1, out_a2; ConvLayer out_c1, out_c2;
+  // filter banks
+  float *pq_fwd = nullptr, *pq_inv = nullptr;
+  int pq_fwd_k = 0, pq_inv_k = 0;
+
+  void finalize(const after_config& c, const TensorMap& tensors, int prec, Arena* ar) {
+    cfg = c; precision = prec; arena = ar; sd = &tensors;
+    M = c.ae_pqmf_bands; n_stages = c.ae_n_stages; nb = c.ae_num_blocks;
+    AFTER_REQUIRE(M == 16 && c.ae_in_channels == 16, AFTER_EINVAL, "codec requires the 16-band PQMF front end (pqmf_bands = in_channels = 16)");
+    AFTER_REQUIRE(n_stages >= 1 && n_stages <= AFTER_MAX_STAGES && nb >= 1 && nb <= AFTER_MAX_STAGES, AFTER_EINVAL, "bad codec stage counts");
+    AFTER_REQUIRE(c.ae_max_samples >= 1 && c.max_batch >= 1, AFTER_EINVAL, "ae_max_samples / max_batch must be >= 1");
+    const int ks = c.ae_kernel_size, G = 8;
+    ech.clear(); dch.clear();
+    for (int i = 0; i <= n_stages; ++i) { ech.push_back(c.ae_channels * c.ae_multipliers[i]); dch.push_back(c.ae_channels * c.ae_dec_multipliers[i]); }
+    ratio = M;
+    for (int i = 0; i < n_stages; ++i) ratio *= c.ae_factors[i];
+
+    // ---- encoder (SimpleNetsStream.py:400-459)
+    make_res(to_in, "encoder.net.0", c.ae_in_channels, ech[0], ks, 1, G, false);
+    downs.resize(n_stages);
+    for (int i = 0; i < n_stages; ++i) {
+      const std::string p = "encoder.net." + std::to_string(i + 1);
+      Down& d = downs[i];
+      d.f = c.ae_factors[i];
+      d.res.resize(nb);
+      for (int j = 0; j < nb; ++j) make_res(d.res[j], p + ".net." + std::to_string(j), ech[i], ech[i], ks, c.ae_dilations[j], G, false);
+      make_snake(d.snake, p + ".net." + std::to_string(nb), ech[i]);
+      make_conv(d.conv, p + ".net." + std::to_string(nb + 1), ech[i], ech[i + 1], 2 * d.f, strided_taps(d.f), d.f);
+    }
+    make_snake(enc_out_snake, "encoder.net." + std::to_string(n_stages + 1), ech[n_stages]);
+    make_conv(enc_out, "encoder.net." + std::to_string(n_stages + 2), ech[n_stages], c.ae_z_channels, 3, conv_taps(3, 1, false), 1);
+
+    // ---- decoder (SimpleNetsStream.py:552-651)
+    make_conv(dec_in, "decoder.net.0", c.ae_z_channels, dch[0], ks, conv_taps(ks, 1, false), 1);
+    ups.resize(n_stages);
+    for (int i = 0; i < n_stages; ++i) {
+      const std::string p = "decoder.net." + std::to_string(i + 1);
+      Up& u = ups[i];
+      u.f = c.ae_factors[n_stages - 1 - i];
+      make_snake(u.snake, p + ".net.0", dch[i]);
+      make_conv_transposed(u.conv, p + ".net.1", dch[i], dch[i + 1], u.f);
+      u.res.resize(nb);
+      for (int j = 0; j < nb; ++j) make_res(u.res[j], p + ".net." + std::to_string(2 + j), dch[i + 1], dch[i + 1], ks, c.ae_dilations[j], G, false);
+    }
+    const int out_c = c.ae_in_channels * (c.ae_use_loudness ? 2 : 1);
+    make_gn_snake(out_a1, "decoder.synth.branches.0.net.0", dch[n_stages], G);
+    make_conv(out_c1, "decoder.synth.branches.0.net.0.net.2", dch[n_stages], out_c, ks, conv_taps(ks, 1, false), 1);
+    make_gn_snake(out_a2, "decoder.synth.branches.0.net.1", out_c, 8);
+    make_conv(out_c2, "decoder.synth.branches.0.net.1.net.2", out_c, out_c, 1, conv_taps(1, 1, false), 1);
+
+    // ---- PQMF banks (pqmf.py:186-279): forward (M, 1, K) -> [K][M]; inverse (M, M, K) -> [K][c][m]
+    {
+      const HostTensor& f = get("pqmf.forward_conv.weight");
+      AFTER_REQUIRE(f.shape.size() == 3 && f.shape[0] == M && f.shape[1] == 1, AFTER_ESHAPE, "pqmf.forward_conv.weight has an unexpected shape");
+      pq_fwd_k = (int)f.shape[2];
+      std::vector<float> wt((size_t)pq_fwd_k * M);
+      for (int m = 0; m < M; ++m)
+        for (int k = 0; k < pq_fwd_k; ++k) wt[(size_t)k * M + m] = f.data[(size_t)m * pq_fwd_k + k];
+      pq_fwd = arena->upload(wt);
+      const HostTensor& v = get("pqmf.inverse_conv.weight");
+      AFTER_REQUIRE(v.shape.size() == 3 && v.shape[0] == M && v.shape[1] == M, AFTER_ESHAPE, "pqmf.inverse_conv.weight has an unexpected shape");
+      pq_inv_k = (int)v.shape[2];
+      std::vector<float> it((size_t)pq_inv_k * M * M);
+      for (int m = 0; m < M; ++m)
+        for (int cc = 0; cc < M; ++cc)
+          for (int k = 0; k < pq_inv_k; ++k) it[((size_t)k * M + cc) * M + m] = v.data[((size_t)m * M + cc) * pq_inv_k + k];
+      pq_inv = arena->upload(it);
+      const size_t smem_a = ((size_t)pq_fwd_k * M + PQ_FRAMES * M + pq_fwd_k) * sizeof(float);
+      const size_t smem_s = ((size_t)pq_inv_k * M * M + (size_t)(PS_FRAMES + pq_inv_k - 1) * M) * sizeof(float);
+      AFTER_REQUIRE(smem_a <= 200 * 1024 && smem_s <= 200 * 1024, AFTER_EINVAL, "PQMF filters too long for shared memory");
+      AFTER_CUDA_CHECK(cudaFuncSetAttribute(pqmf_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+      AFTER_CUDA_CHECK(cudaFuncSetAttribute(pqmf_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    }
+
+    // ---- workspace: the largest activation (frames x channels) of either net at the longest input
+    AFTER_REQUIRE(c.ae_max_samples % ratio == 0, AFTER_EINVAL, "ae_max_samples must be a multiple of the codec ratio");
+    size_t T = (size_t)(c.ae_max_samples / M), mx = T * std::max(c.ae_in_channels, out_c);
+    for (int i = 0; i <= n_stages; ++i) {
+      mx = std::max(mx, T * (size_t)ech[i]);
+      if (i < n_stages) T /= c.ae_factors[i];
+    }
+    mx = std::max(mx, T * (size_t)c.ae_z_channels);
+    for (int i = 0; i <= n_stages; ++i) {
+      mx = std::max(mx, T * (size_t)dch[i]);
+      if (i < n_stages) T *= c.ae_factors[n_stages - 1 - i];
+    }
+    alloc_workspace(mx, c.max_batch, 2 * (n_stages * nb + 4) + 8);
+    AFTER_CUDA_CHECK(cudaDeviceSynchronize());
+    sd = nullptr;
+  }
+
+  void destroy() { graphs.destroy(); }
+
+  void check(int B, int64_t samples) {
+    AFTER_REQUIRE(B >= 1 && B <= maxB, AFTER_EINVAL, "batch exceeds max_batch given at after_create");
+    AFTER_REQUIRE(samples >= ratio && samples % ratio == 0, AFTER_EINVAL, "samples must be a positive multiple of the codec ratio");
+    AFTER_REQUIRE(samples <= cfg.ae_max_samples, AFTER_EINVAL, "samples exceed ae_max_samples given at after_create");
+  }
+
+  // ------------------------------------------------------------------ AutoEncoder.encode
+  void encode_body(const float* audio, float* z, int B, int64_t samples, cudaStream_t st) {
+    begin(st);
+    int T = (int)(samples / M);
+    float *x = buf[0], *y1 = buf[1], *o = buf[2];
+    {
+      dim3 grid(ceil_div(T, PQ_FRAMES), B);
+      const size_t smem = ((size_t)pq_fwd_k * M + PQ_FRAMES * M + pq_fwd_k) * sizeof(float);
+      const int p = (pq_fwd_k - 1) + 1;  // get_padding(k): left = (p - 1) / 2
+      pqmf_analysis_kernel<<<grid, 256, smem, st>>>(audio, pq_fwd, x, T, pq_fwd_k, (p - 1) / 2);
+      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    }
+    double* xs = new_slot();
+    gn_stats_launch(x, xs, B, T, cfg.ae_in_channels, to_in.a1.groups, st);
+    double* os = new_slot();
+    res_block(to_in, x, xs, y1, o, os, 8, B, T, st);
+    std::swap(x, o); xs = os;
+    for (int i = 0; i < n_stages; ++i) {
+      Down& d = downs[i];
+      for (int j = 0; j < nb; ++j) {
+        const bool need = j + 1 < nb;  // the stage's last block feeds a bare Snake, not a GroupNorm
+        os = need ? new_slot() : nullptr;
+        res_block(d.res[j], x, xs, y1, o, os, 8, B, T, st);
+        std::swap(x, o); xs = os;
+      }
+      produce(x, d.snake, nullptr, d.conv, B, T, ech[i], st);
+      T /= d.f;
+      const bool need = i + 1 < n_stages;  // next stage starts with a GroupNorm; after the last one a Snake follows
+      os = need ? new_slot() : nullptr;
+      conv(d.conv, B, T, o, nullptr, os, 8, st);
+      std::swap(x, o); xs = os;
+    }
+    produce(x, enc_out_snake, nullptr, enc_out, B, T, ech[n_stages], st);
+    conv(enc_out, B, T, o, nullptr, nullptr, 1, st);
+    // ReluBottleneck is the identity at inference (SimpleNetsStream.py:753-760); public layout is channel-first
+    dim3 grid(ceil_div(T, 32), ceil_div(cfg.ae_z_channels, 32), B);
+    tokens_to_channels_kernel<<<grid, 256, 0, st>>>(o, z, cfg.ae_z_channels, T);
+    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+  }
+
+  void encode(const float* audio, float* z, int B, int64_t samples, cudaStream_t st) {
+    check(B, samples);
+    // graph nodes bake the I/O pointers in: key on them too
+    graphs.run({0, B, (int)(samples & 0x7fffffff), (int)((uintptr_t)audio & 0x7fffffff), (int)((uintptr_t)audio >> 31),
+                (int)((uintptr_t)z & 0x7fffffff), (int)((uintptr_t)z >> 31)},
+               st, [&] { encode_body(audio, z, B, samples, st); });
+  }
+
+  // ------------------------------------------------------------------ AutoEncoder.decode
+  void decode_body(const float* z, float* audio, int B, int Tz, cudaStream_t st) {
+    begin(st);
+    int T = Tz;
+    float *x = buf[0], *y1 = buf[1], *o = buf[2];
+    {
+      dim3 grid(ceil_div(T, 32), ceil_div(cfg.ae_z_channels, 32), B);
+      channels_to_frames_kernel<<<grid, 256, 0, st>>>(z, o, cfg.ae_z_channels, T);
+      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    }
+    NormAct ident;
+    produce(o, ident, nullptr, dec_in, B, T, cfg.ae_z_channels, st);
+    conv(dec_in, B, T, x, nullptr, nullptr, 1, st);
+    double *xs = nullptr, *os = nullptr;
+    for (int i = 0; i < n_stages; ++i) {
+      Up& u = ups[i];
+      produce(x, u.snake, nullptr, u.conv, B, T, dch[i], st);
+      os = new_slot();
+      conv(u.conv, B, T, o, nullptr, os, 8, st);
+      T *= u.f;
+      std::swap(x, o); xs = os;
+      for (int j = 0; j < nb; ++j) {
+        // after a stage's last block comes a bare Snake (next stage) -- except the final stage, whose output
+        // feeds the GroupNorm of the synthesis head
+        const bool need = j + 1 < nb || i + 1 == n_stages;
+        os = need ? new_slot() : nullptr;
+        res_block(u.res[j], x, xs, y1, o, os, std::min(dch[i + 1], 8), B, T, st);
+        std::swap(x, o); xs = os;
+      }
+    }
+    // synthesis head: two ConvBlock1d without residual (SimpleNetsStream.py:612-633), loudness gate, inverse PQMF
+    os = new_slot();
+    produce(x, out_a1, xs, out_c1, B, T, dch[n_stages], st);
+    conv(out_c1, B, T, y1, nullptr, os, out_a2.groups, st);
+    produce(y1, out_a2, os, out_c2, B, T, out_c2.cin, st);
+    conv(out_c2, B, T, o, nullptr, nullptr, 1, st);
+    {
+      dim3 grid(ceil_div(T, PS_FRAMES), B);
+      const size_t smem = ((size_t)pq_inv_k * M * M + (size_t)(PS_FRAMES + pq_inv_k - 1) * M) * sizeof(float);
+      pqmf_synthesis_kernel<<<grid, 256, smem, st>>>(o, pq_inv, audio, T, pq_inv_k, (pq_inv_k - 1) / 2, cfg.ae_use_loudness);
+      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    }
+  }
+
+  void decode(const float* z, float* audio, int B, int T, cudaStream_t st) {
+    AFTER_REQUIRE(T >= 1, AFTER_EINVAL, "T must be >= 1");
+    check(B, (int64_t)T * ratio);
+    graphs.run({1, B, T, (int)((uintptr_t)audio & 0x7fffffff), (int)((uintptr_t)audio >> 31), (int)((uintptr_t)z & 0x7fffffff),
+                (int)((uintptr_t)z >> 31)},
+               st, [&] { decode_body(z, audio, B, T, st); });
+  }
+};
+
+// ===========================================================================================
+// Encoder1D (structure encoder), all ratios == 1   (encoder.py:74-113, 116-237, 273-298)
+struct StructureEncoder : ConvNet {
+  after_config cfg{};
+  struct Block { NormAct a1, a2; ConvLayer c1, c2; };
+  std::vector<Block> blocks;   // n + 1 V2ConvBlock1D
+  std::vector<ConvLayer> pools;  // n 1x1 convs
+  std::vector<int> cins, couts;
+  int n = 0, maxT = 0;
+
+  void make_block(Block& b, const std::string& prefix, int C, int k, bool causal) {
+    make_bn_silu(b.a1, prefix + ".net.branches.0.0", C);
+    make_conv(b.c1, prefix + ".net.branches.0.2", C, C, k, conv_taps(k, 1, causal), 1);
+    make_bn_silu(b.a2, prefix + ".net.branches.0.3", C);
+    make_conv(b.c2, prefix + ".net.branches.0.6", C, C, k, conv_taps(k, 1, causal), 1);
+  }
+
+  void finalize(const after_config& c, const TensorMap& tensors, int prec, Arena* ar) {
+    cfg = c; precision = prec; arena = ar; sd = &tensors;
+    n = c.se_n_blocks;
+    AFTER_REQUIRE(n >= 1 && n <= AFTER_MAX_STAGES, AFTER_EINVAL, "bad structure-encoder block count");
+    cins.clear(); couts.clear();
+    for (int i = 0; i < n; ++i) { cins.push_back(i == 0 ? c.se_in_size : c.se_channels[i - 1]); couts.push_back(c.se_channels[i]); }
+    blocks.resize(n + 1);
+    pools.resize(n);
+    int mxc = c.se_in_size;
+    for (int i = 0; i < n; ++i) {
+      const std::string p = "net." + std::to_string(i);
+      make_block(blocks[i], p + ".net.0", cins[i], c.se_kernel_size, c.se_causal != 0);
+      make_conv(pools[i], p + ".net.1", cins[i], couts[i], 1, conv_taps(1, 1, false), 1);
+      mxc = std::max(mxc, std::max(cins[i], couts[i]));
+    }
+    make_block(blocks[n], "net." + std::to_string(n), couts[n - 1], c.se_kernel_size, c.se_causal != 0);
+    maxT = c.seq_len;
+    alloc_workspace((size_t)maxT * mxc, c.max_batch, 1);
+    AFTER_CUDA_CHECK(cudaDeviceSynchronize());
+    sd = nullptr;
+  }
+
+  // x + conv(SiLU(BN(conv(SiLU(BN(x))))))   (encoder.py:25-71, dropout off)
+  void run_block(const Block& b, const float* x, float* y1, float* out, int B, int T, cudaStream_t st) {
+    produce(x, b.a1, nullptr, b.c1, B, T, b.c1.cin, st);
+    conv(b.c1, B, T, y1, nullptr, nullptr, 1, st);
+    produce(y1, b.a2, nullptr, b.c2, B, T, b.c2.cin, st);
+    conv(b.c2, B, T, out, x, nullptr, 1, st);
+  }
+
+  void forward_body(const float* z, float* out, int B, int T, cudaStream_t st) {
+    float *x = buf[0], *y1 = buf[1], *o = buf[2];
+    {
+      dim3 grid(ceil_div(T, 32), ceil_div(cfg.se_in_size, 32), B);
+      channels_to_frames_kernel<<<grid, 256, 0, st>>>(z, x, cfg.se_in_size, T);
+      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    }
+    NormAct ident;
+    for (int i = 0; i < n; ++i) {
+      run_block(blocks[i], x, y1, o, B, T, st);
+      produce(o, ident, nullptr, pools[i], B, T, cins[i], st);
+      conv(pools[i], B, T, x, nullptr, nullptr, 1, st);
+    }
+    run_block(blocks[n], x, y1, o, B, T, st);
+    const int C = couts[n - 1];
+    if (cfg.se_use_tanh) {
+      const size_t nel = (size_t)B * T * C;
+      tanh_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(o, nel);
+      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    }
+    dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B);
+    tokens_to_channels_kernel<<<grid, 256, 0, st>>>(o, out, C, T);
+    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+  }
+
+  void forward(const float* z, float* out, int B, int T, cudaStream_t st) {
+    AFTER_REQUIRE(B >= 1 && B <= maxB, AFTER_EINVAL, "batch exceeds max_batch given at after_create");
+    AFTER_REQUIRE(T >= 1 && T <= maxT, AFTER_EINVAL, "T exceeds seq_len given at after_create");
+    forward_body(z, out, B, T, st);
+  }
+  void destroy() { graphs.destroy(); }
+};
+
 }  // namespace after

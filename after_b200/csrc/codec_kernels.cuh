@@ -1,0 +1,259 @@
+// Element-wise / filter-bank kernels of the codec (after/autoencoder/networks/SimpleNetsStream.py, pqmf.py,
+// after/autoencoder/core.py) and of the structure encoder (after/diffusion/networks/encoder.py).
+// All activations are frame-major fp32 (B, T, C); convolutions themselves are tap-GEMMs (gemm.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace after {
+
+enum NormMode { NORM_NONE = 0, NORM_GROUP = 1, NORM_AFFINE = 2 };
+enum ActMode { ACT_NONE = 0, ACT_SNAKE = 1, ACT_SILU = 2 };
+
+struct ActParams {
+  int norm = NORM_NONE;
+  int act = ACT_NONE;
+  // NORM_GROUP: GroupNorm(groups, C, eps=1e-5, affine) over (C/groups x T) per stream, biased variance
+  //             (SimpleNetsStream.py:95-147 offline branch; statistics come from the producer's epilogue)
+  const double* stats = nullptr;  // [B][groups][2] = sum, sum of squares
+  int groups = 1;
+  const float* gamma = nullptr;   // [C]
+  const float* beta = nullptr;    // [C]
+  // NORM_AFFINE: y = (x - mu[c]) * rs[c] + be[c]   (eval-mode BatchNorm, encoder.py:39-48; folded at load)
+  const float* mu = nullptr;
+  const float* rs = nullptr;
+  const float* be = nullptr;
+  // ACT_SNAKE: y + sin^2(alpha y) * inv_beta,  inv_beta = 1 / (beta + 1e-9)   (core.py:217-218)
+  const float* alpha = nullptr;
+  const float* inv_beta = nullptr;
+};
+
+struct OperandOut {
+  float* f32 = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+};
+
+__device__ __forceinline__ float snake_beta(float y, float a, float ib) {
+  const float s = sinf(y * a);
+  return fmaf(s * s, ib, y);
+}
+__device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
+
+// x (B, T, C) fp32 -> operand (B, T, C): act(norm(x)).  grid = (ceil(T / frames_per_block), B), 256 threads.
+// C % 4 == 0 is required for the vector path (C4 = C / 4 float4 per frame); a scalar variant handles the rest.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int frames_per_block) {
+  extern __shared__ float sm[];  // mu[C], rs[C], be[C], al[C], ib[C]
+  float* s_mu = sm;
+  float* s_rs = sm + C;
+  float* s_be = sm + 2 * C;
+  float* s_al = sm + 3 * C;
+  float* s_ib = sm + 4 * C;
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mu = 0.f, rs = 1.f, be = 0.f;
+    if (p.norm == NORM_GROUP) {
+      const int cpg = C / p.groups;
+      const int g = c / cpg;
+      const double n = (double)cpg * (double)T;
+      const double s = p.stats[((size_t)b * p.groups + g) * 2];
+      const double q = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      mu = (float)mean;
+      rs = (float)(1.0 / sqrt(var + 1e-5)) * p.gamma[c];
+      be = p.beta[c];
+    } else if (p.norm == NORM_AFFINE) {
+      mu = p.mu[c]; rs = p.rs[c]; be = p.be[c];
+    }
+    s_mu[c] = mu; s_rs[c] = rs; s_be[c] = be;
+    s_al[c] = p.act == ACT_SNAKE ? p.alpha[c] : 0.f;
+    s_ib[c] = p.act == ACT_SNAKE ? p.inv_beta[c] : 0.f;
+  }
+  __syncthreads();
+  const int t0 = blockIdx.x * frames_per_block;
+  const int nt = min(frames_per_block, T - t0);
+  const size_t base = ((size_t)b * T + t0) * C;
+  const int per_frame = C / VEC;
+  const int total = nt * per_frame;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = (i % per_frame) * VEC;
+    const size_t off = base + (size_t)i * VEC;
+    float v[VEC];
+    if (VEC == 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      v[0] = xv.x; v[1 % VEC] = xv.y; v[2 % VEC] = xv.z; v[3 % VEC] = xv.w;
+    } else {
+      v[0] = x[off];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float y = (v[j] - s_mu[c + j]) * s_rs[c + j] + s_be[c + j];
+      if (p.act == ACT_SNAKE) y = snake_beta(y, s_al[c + j], s_ib[c + j]);
+      else if (p.act == ACT_SILU) y = silu(y);
+      v[j] = y;
+    }
+    if (VEC == 4) {
+      if (out.f32) *reinterpret_cast<float4*>(out.f32 + off) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+      if (out.hi) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(v[j % VEC], h[j], l[j]);
+        *reinterpret_cast<uint2*>(out.hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        if (out.lo) *reinterpret_cast<uint2*>(out.lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      }
+    } else {
+      if (out.f32) out.f32[off] = v[0];
+      if (out.hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v[0], h, l);
+        out.hi[off] = h;
+        if (out.lo) out.lo[off] = l;
+      }
+    }
+  }
+}
+
+// Stand-alone GroupNorm statistics of x (B, T, C): stats[b][g] += {sum, sum of squares}.  Used where the producer
+// is not a tap-GEMM epilogue (PQMF output, naive-kernel layers).  grid = (ceil(T / 256), B), 256 threads.
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int T, int C, int groups) {
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 256;
+  const int nt = min(256, T - t0);
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* p = x + ((size_t)b * T + t0) * C + c;
+    float s = 0.f, q = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const float v = p[(size_t)t * C];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    double* d = stats + ((size_t)b * groups + c / cpg) * 2;
+    atomicAdd(d, (double)s);
+    atomicAdd(d + 1, (double)q);
+  }
+}
+
+// channel-first (B, C, T) <-> frame-major (B, T, C) fp32 (the reference's public layouts are channel-first)
+__global__ void __launch_bounds__(256)
+channels_to_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? in[((size_t)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (c < C && t < T) out[((size_t)b * T + t) * C + c] = tile[tx][i];
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// PQMF analysis (pqmf.py:263-271, 286-290): out[b, t, m] = sum_k hk[m, k] * x[b, M t + k - pad_l], then negate
+// odd bands at even frames (reverse_half, pqmf.py:16-20).  wT: [K][M] transposed filter bank.
+// block = 64 frames x M(=16) bands, 256 threads: thread -> band (tid & 15), 4 frames.
+// -------------------------------------------------------------------------------------------
+constexpr int PQ_FRAMES = 64;
+
+__global__ void __launch_bounds__(256)
+pqmf_analysis_kernel(const float* __restrict__ audio, const float* __restrict__ wT, float* __restrict__ out, int T,
+                     int K, int pad_l) {
+  constexpr int M = 16;
+  extern __shared__ float sm[];
+  float* s_w = sm;                  // [K][M]
+  float* s_x = sm + (size_t)K * M;  // [PQ_FRAMES * M + K]
+  const int b = blockIdx.y, t0 = blockIdx.x * PQ_FRAMES;
+  const int64_t S = (int64_t)T * M;
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) s_w[i] = wT[i];
+  const int seg = PQ_FRAMES * M + K;
+  const int64_t s0 = (int64_t)t0 * M - pad_l;
+  for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+    const int64_t s = s0 + i;
+    s_x[i] = (s >= 0 && s < S) ? audio[(size_t)b * S + s] : 0.f;
+  }
+  __syncthreads();
+  const int m = threadIdx.x & 15, fg = threadIdx.x >> 4;  // fg: 0..15 -> frames fg*4..fg*4+3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xs = s_x + fg * 4 * M;
+  for (int k = 0; k < K; ++k) {
+    const float w = s_w[k * M + m];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) acc[f] = fmaf(w, xs[f * M + k], acc[f]);
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int t = t0 + fg * 4 + f;
+    if (t < T) {
+      const float v = ((m & 1) && !(t & 1)) ? -acc[f] : acc[f];
+      out[((size_t)b * T + t) * M + m] = v;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Loudness gate + PQMF synthesis (SimpleNetsStream.py:644-646, pqmf.py:292-301):
+//   u (B, T, 2M) -> g[c] = u[c] * sigmoid(u[M + c])            (use_loudness; else u is (B, T, M))
+//   xs[c, t] = g[c, t] * (-1 if c odd and t even)
+//   y[m, t] = M * sum_{c,k} w[m, c, k] xs[c, t + k - pad_l] ;  audio[b, t*M + (M-1-m)] = y[m, t]
+// wT: [K][M(c)][M(m)].  block = 128 frames, 256 threads: thread -> band m (tid & 15), 8 frames.
+// -------------------------------------------------------------------------------------------
+constexpr int PS_FRAMES = 128;
+
+__global__ void __launch_bounds__(256)
+pqmf_synthesis_kernel(const float* __restrict__ u, const float* __restrict__ wT, float* __restrict__ audio, int T,
+                      int K, int pad_l, int loud) {
+  constexpr int M = 16;
+  extern __shared__ float sm[];
+  float* s_w = sm;                      // [K][M][M]
+  float* s_x = sm + (size_t)K * M * M;  // [(PS_FRAMES + K - 1)][M]
+  const int b = blockIdx.y, t0 = blockIdx.x * PS_FRAMES;
+  for (int i = threadIdx.x; i < K * M * M; i += blockDim.x) s_w[i] = wT[i];
+  const int rows = PS_FRAMES + K - 1;
+  const int ld = loud ? 2 * M : M;
+  for (int i = threadIdx.x; i < rows * M; i += blockDim.x) {
+    const int r = i / M, c = i % M;
+    const int t = t0 + r - pad_l;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const float* row = u + ((size_t)b * T + t) * ld;
+      v = row[c];
+      if (loud) v *= 1.0f / (1.0f + expf(-row[M + c]));
+      if ((c & 1) && !(t & 1)) v = -v;
+    }
+    s_x[i] = v;
+  }
+  __syncthreads();
+  const int m = threadIdx.x & 15, fg = threadIdx.x >> 4;  // frames fg*8 .. fg*8+7
+  float acc[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* xr = s_x + (size_t)(fg * 8 + k) * M;
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      const float w = s_w[(k * M + c) * M + m];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) acc[f] = fmaf(w, xr[f * M + c], acc[f]);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    const int t = t0 + fg * 8 + f;
+    if (t < T) audio[(size_t)b * T * M + (size_t)t * M + (M - 1 - m)] = acc[f] * (float)M;
+  }
+}
+
+// tanh epilogue of the structure encoder when use_tanh is set (encoder.py:296-297)
+__global__ void tanh_kernel(float* __restrict__ x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = tanhf(x[i]);
+}
+
+}  // namespace after
