@@ -18,6 +18,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_simt": PRECI
 DTYPE_F32, DTYPE_F64, DTYPE_I64 = 0, 1, 2
 MODULE_DENOISER, MODULE_AUTOENCODER, MODULE_STRUCTURE_ENCODER, MODULE_TIMBRE_ENCODER = 0, 1, 2, 3
 CFG_AUDIO, CFG_MIDI = 0, 1
+KERNEL_CLASSES = {"tap_gemm_tc": 0, "tap_gemm_simt": 1, "attention": 2, "row_norm": 3, "act_operand": 4, "pqmf": 5}
 
 
 class AfterConfig(C.Structure):
@@ -85,6 +86,9 @@ PROTOTYPES = {
     "after_launch_count": (C.c_int64, [_H]),
     "after_device_bytes": (C.c_int64, [_H]),
     "after_ae_ratio": (C.c_int, [_H]),
+    "after_profile_enable": (C.c_int, [_H, C.c_int]),
+    "after_profile_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
     "after_debug_gemm": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -10,6 +10,7 @@
 
 namespace after {
 std::atomic<int64_t> g_launches{0};
+Profiler g_prof;
 }
 
 using namespace after;
@@ -330,6 +331,23 @@ int after_ae_ratio(after_handle h) {
   int r = h->cfg.ae_pqmf_bands > 0 ? h->cfg.ae_pqmf_bands : 1;
   for (int i = 0; i < h->cfg.ae_n_stages; ++i) r *= h->cfg.ae_factors[i];
   return r;
+}
+
+int after_profile_enable(after_handle h, int on) {
+  return guarded(h, [&] {
+    AFTER_CUDA_CHECK(cudaDeviceSynchronize());
+    g_prof.reset();
+    g_prof.on = on != 0;
+  });
+}
+
+int after_profile_read(after_handle h, int kernel_class, int64_t* launches, double* ms, double* flops, double* bytes) {
+  return guarded(h, [&] {
+    AFTER_REQUIRE(kernel_class >= 0 && kernel_class < KC_COUNT, AFTER_EINVAL, "unknown kernel class");
+    AFTER_REQUIRE(launches && ms && flops && bytes, AFTER_EINVAL, "null output pointer");
+    AFTER_CUDA_CHECK(cudaDeviceSynchronize());
+    g_prof.read(kernel_class, launches, ms, flops, bytes);
+  });
 }
 
 int after_debug_gemm(after_handle h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,

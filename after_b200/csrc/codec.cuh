@@ -37,7 +37,7 @@ struct GraphCache {
   }
   template <typename F>
   void run(const std::vector<int>& key, cudaStream_t st, F&& body) {
-    if (!enabled) {
+    if (!enabled || g_prof.on) {
       body();
       return;
     }
@@ -280,6 +280,8 @@ struct ConvNet {
     const int fpb = std::max(1, 16384 / C);
     dim3 grid(ceil_div(T, fpb), B);
     const size_t smem = (size_t)5 * C * sizeof(float);
+    const double el = (double)B * T * C;
+    ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 + (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
     if (C % 4 == 0) act_operand_kernel<4><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
     else act_operand_kernel<1><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
     AFTER_CUDA_CHECK(cudaGetLastError());
@@ -453,6 +455,7 @@ struct Codec : ConvNet {
       dim3 grid(ceil_div(T, PQ_FRAMES), B);
       const size_t smem = ((size_t)pq_fwd_k * M + PQ_FRAMES * M + pq_fwd_k) * sizeof(float);
       const int p = (pq_fwd_k - 1) + 1;  // get_padding(k): left = (p - 1) / 2
+      ProfScope prof(KC_PQMF, st, 2.0 * B * T * M * pq_fwd_k, (double)B * T * M * 8.0);
       pqmf_analysis_kernel<<<grid, 256, smem, st>>>(audio, pq_fwd, x, T, pq_fwd_k, (p - 1) / 2);
       AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
     }
@@ -531,6 +534,7 @@ struct Codec : ConvNet {
     {
       dim3 grid(ceil_div(T, PS_FRAMES), B);
       const size_t smem = ((size_t)pq_inv_k * M * M + (size_t)(PS_FRAMES + pq_inv_k - 1) * M) * sizeof(float);
+      ProfScope prof(KC_PQMF, st, 2.0 * B * T * M * M * pq_inv_k, (double)B * T * M * (cfg.ae_use_loudness ? 12.0 : 8.0));
       pqmf_synthesis_kernel<<<grid, 256, smem, st>>>(o, pq_inv, audio, T, pq_inv_k, (pq_inv_k - 1) / 2, cfg.ae_use_loudness);
       AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
     }

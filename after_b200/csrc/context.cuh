@@ -14,6 +14,56 @@ namespace after {
 extern std::atomic<int64_t> g_launches;
 #define AFTER_COUNT_LAUNCH() (::after::g_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Per-kernel-class device timing for the roofline report: CUDA events recorded on the launching (work) stream
+// around every launch of the profiled classes.  While enabled, graph replay is bypassed (events inside a
+// captured graph cannot be timed), so the numbers are per-launch durations of the very same kernels.
+enum KernelClass {
+  KC_TAP_GEMM_TC = 0, KC_TAP_GEMM_SIMT = 1, KC_ATTENTION = 2, KC_ROW_NORM = 3, KC_ACT_OPERAND = 4, KC_PQMF = 5,
+  KC_OTHER = 6, KC_COUNT = 7
+};
+
+struct Profiler {
+  bool on = false;
+  struct Rec { int cls; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    AFTER_CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+  }
+  void reset() {
+    for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear();
+  }
+  // sums over finished records of one class; caller synchronises the device first
+  void read(int cls, int64_t* n, double* ms, double* flops, double* bytes) {
+    *n = 0; *ms = 0; *flops = 0; *bytes = 0;
+    for (auto& r : recs) {
+      if (r.cls != cls) continue;
+      float t = 0.f;
+      AFTER_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+      *n += 1; *ms += t; *flops += r.flops; *bytes += r.bytes;
+    }
+  }
+};
+extern Profiler g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  bool active;
+  ProfScope(int cls, cudaStream_t s, double flops, double bytes) : st(s), active(g_prof.on) {
+    if (!active) return;
+    Profiler::Rec r{cls, g_prof.get(), g_prof.get(), flops, bytes};
+    cudaEventRecord(r.a, st);
+    g_prof.recs.push_back(r);
+  }
+  ~ProfScope() {
+    if (active) cudaEventRecord(g_prof.recs.back().b, st);
+  }
+};
+
 struct HostTensor {
   std::vector<int64_t> shape;
   std::vector<float> data;

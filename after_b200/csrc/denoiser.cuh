@@ -224,6 +224,7 @@ struct Denoiser {
   template <int NV>
   void launch_adaln_t(const float* hin, int use_src, int l, int rows, int T, cudaStream_t st) {
     RowOperandOut o = operand_out(a_op);
+    ProfScope prof(KC_ROW_NORM, st, 0.0, (double)rows * D * (tc_mode() ? 4.0 * 2 + 2.0 * (nprod() > 1 ? 2 : 1) : 12.0));
     adaln_t_ln1_kernel<NV><<<ceil_div(rows, 8), 256, 0, st>>>(hin, h, o, adaT, L * 2 * D, l * 2 * D, seqmap(), use_src,
                                                              layers[l].n1_g, layers[l].n1_b, rows, T);
     AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
@@ -231,6 +232,9 @@ struct Denoiser {
   template <int NH, int MAXK>
   void launch_attn(int l, const float* adaC_step, int rows, int T, cudaStream_t st) {
     RowOperandOut o = operand_out(a_op);
+    // q,k,v read once + h read/write + operand write; ~2 * keys * 64 * 2 flops per (token, head)
+    ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
+                   (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
     attn_adaln_c_ln3_kernel<NH, MAXK><<<ceil_div(rows, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
                                                                          layers[l].n3_g, layers[l].n3_b, rows, T,
                                                                          cfg.attention_chunk_size, cfg.local_attention_size);
@@ -428,7 +432,7 @@ struct Denoiser {
     cfg_maps(B, T, variant, st);  // synchronises: tg stays alive until here
     set_guidance(g_t, g_s, variant, clamp, 1.0f / (float)nb_steps, st);
 
-    if (!use_graph) {
+    if (!use_graph || g_prof.on) {
       sample_body(B, T, nb_steps, st);
     } else {
       auto key = std::make_tuple(B, T, nb_steps, variant, 0);

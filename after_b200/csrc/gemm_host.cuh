@@ -165,6 +165,11 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
                      cudaStream_t st) {
   const bool tc_mode = precision != AFTER_PRECISION_FP32_SIMT;
   epi.bias = W.bias;
+  // algorithmic work of this launch: 2*M*N*K flops; operand read once + result written once (+ residual read)
+  const double rows = (double)B * T;
+  const double g_flops = 2.0 * rows * W.N * W.K;
+  const double g_bytes = rows * P * W.Cin * 4.0 + rows * W.N * 4.0 * (epi.res ? 2.0 : 1.0);
+  ProfScope prof(tc_mode && W.tc_ok ? KC_TAP_GEMM_TC : KC_TAP_GEMM_SIMT, st, g_flops, g_bytes);
   if (tc_mode && W.tc_ok) {
     AFTER_REQUIRE(A.hi != nullptr, AFTER_ESTATE, "operand has no bf16 copy");
     const int nprod = precision == AFTER_PRECISION_BF16 ? 1 : 3;

@@ -269,6 +269,19 @@ class Engine:
                     "after_structure_encode")
         return out
 
+    def profile(self, on: bool):
+        L.check(self._lib.after_profile_enable(self._h, int(on)), self._h, "after_profile_enable")
+
+    def profile_read(self):
+        """{class: {launches, ms, flops, bytes}} accumulated since ``profile(True)``."""
+        out = {}
+        for name, k in L.KERNEL_CLASSES.items():
+            n, ms, fl, by = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+            L.check(self._lib.after_profile_read(self._h, k, C.byref(n), C.byref(ms), C.byref(fl), C.byref(by)), self._h,
+                    "after_profile_read")
+            out[name] = {"launches": n.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
+        return out
+
     def debug_gemm(self, A, W, bias=None, precision="fp32"):
         A = self._dev(A, "A")
         W = self._dev(W, "W")

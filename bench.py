@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the AFTER latent-sampling hot path on B200 (contract: see the task brief / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): base audio-to-audio, batch = 8 streams per GPU, 50 Euler steps x 3-way CFG
+over one 524288-sample chunk per stream (T = 256 latent frames), synthetic seeded weights and inputs.
+One bench "step" = one ``RectifiedFlow.sample`` call (50 diffusion steps over the per-GPU batch).
+``value`` = diffusion-steps/s summed over GPUs (each GPU integrates its own 8 streams: weak scaling), inputs
+resident in HBM; ``e2e`` = the same through the host-buffer C-ABI entry (pinned host tensors, H2D + D2H inside);
+``rtf`` = real-time factor of the full chain (2x encode, structure encoder, sample, decode).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK = 524288
+SR = 44100
+FLOP_PER_SEQ = {"base": 7.36e9, "tiny": 1.86e9, "midi": 7.75e9}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_setup(name, B_total):
+    from after_b200 import config, synth
+    mc = config.get_config(name)
+    x0, cond, tc = synth.synth_inputs(B_total, mc.denoiser, seed=1234)
+    return mc, x0, cond, tc
+
+
+def cpu_reference_steps_per_s(name, B, nb_steps, repeats=1, threads=None):
+    """The CPU restatement of the reference's sampler (oracle port, plain PyTorch CPU ops) on this host."""
+    import torch
+    from after_b200 import synth
+    from oracle import after_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mc, x0, cond, tc = synth_setup(name, B)
+    sd = synth.denoiser_state_dict(mc.denoiser, 0)
+    O.sample(sd, mc.denoiser, x0[:1], cond[:1], tc[:1], 1, 2.0, 1.0)  # warm the thread pool / allocator
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.sample(sd, mc.denoiser, x0, cond, tc, nb_steps, 2.0, 1.0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nb_steps / best, threads, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_steps = 2  # bounded sample of the 50-step workload: every diffusion step is identical work
+    import torch
+    from after_b200 import synth
+    from oracle import after_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mc, x0, cond, tc = synth_setup(args.model, args.batch)
+    sd = synth.denoiser_state_dict(mc.denoiser, 0)
+    for _ in range(max(args.warmup, 1)):
+        O.sample(sd, mc.denoiser, x0[:1], cond[:1], tc[:1], 1, 2.0, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.sample(sd, mc.denoiser, x0, cond, tc, sample_steps, 2.0, 1.0)
+    dt = time.perf_counter() - t0
+    v = sample_steps * args.steps / dt
+    sample = f"{sample_steps} of {args.nb_steps} diffusion steps per bench step, B={args.batch}, T=256, all host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "diffusion-steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * args.nb_steps / sample_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{args.model} audio-to-audio sampler, batch={args.batch}, {args.nb_steps} steps, T=256, CPU",
+                   "batch_per_gpu": args.batch, "nb_steps": args.nb_steps},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
+    ap.add_argument("--model", default="base", choices=["base", "tiny", "midi"])
+    ap.add_argument("--batch", type=int, default=8, help="streams per GPU")
+    ap.add_argument("--nb-steps", type=int, default=50, help="diffusion (Euler) steps per sample call")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="skip the full-chain RTF leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from after_b200 import build, config, synth
+    from after_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    B, NS = args.batch, args.nb_steps
+    mc, x0_all, cond_all, tc_all = synth_setup(args.model, B * world)  # host-generated once: identical for any N
+    sl = slice(rank * B, (rank + 1) * B)
+    x0_h, cond_h, tc_h = (t[sl].contiguous().pin_memory() for t in (x0_all, cond_all, tc_all))
+    acfg = config.base_autoencoder()
+    den_sd = synth.denoiser_state_dict(mc.denoiser, 0)
+    chain = not args.no_chain
+    ae_sd = synth.autoencoder_state_dict(acfg, 0) if chain else None
+    se_sd = synth.encoder1d_state_dict(mc.structure_encoder, 0) if (chain and mc.structure_encoder is not None) else None
+    eng = Engine(model=mc, autoencoder=acfg if chain else None, denoiser_state=den_sd, autoencoder_state=ae_sd,
+                 structure_state=se_sd, precision=args.precision, device=local, max_batch=B, max_steps=NS, max_samples=CHUNK)
+    x0, cond, tc = x0_h.to(dev), cond_h.to(dev), tc_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gathered = torch.empty(world * B, x0.shape[1], x0.shape[2], device=dev) if world > 1 else None
+
+    def one_step():
+        out = eng.sample(x0, cond, tc, NS, 2.0, 1.0)
+        if world > 1:  # the single collective of the path: gather the generated latents
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+
+    def timed(fn, K):
+        """K steps, L2 flushed before each, per-step CUDA events on the current stream; returns total ms (max over ranks)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        per = [a.elapsed_time(b) for a, b in evs]
+        tot = torch.tensor([sum(per)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), per
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count
+    total_ms, per = timed(one_step, args.steps)
+    launches = eng.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = NS * args.steps * world / (total_ms / 1e3)
+
+    # ---- end to end through the host-buffer C-ABI entry (H2D of x0/cond/time_cond, D2H of the latents inside) ----
+    out_h = torch.empty_like(x0_h).pin_memory()
+
+    def host_step():
+        eng.sample_host(x0_h, cond_h, tc_h, out_h, NS, 2.0, 1.0)
+
+    host_step()
+    e2e_ms, _ = timed(host_step, args.steps)
+    e2e = {"value": NS * args.steps * world / (e2e_ms / 1e3), "unit": "steps/s",
+           "h2d_bytes_per_step": int(4 * (x0_h.numel() + cond_h.numel() + tc_h.numel())),
+           "d2h_bytes_per_step": int(4 * out_h.numel())}
+
+    # ---- full chain: real-time factor -----------------------------------------------------------------------------
+    rtf = None
+    if chain:
+        audio_s = synth.synth_audio(B, CHUNK, seed=7 + rank).to(dev)   # structure source
+        audio_t = synth.synth_audio(B, CHUNK, seed=107 + rank).to(dev)  # timbre source
+
+        def chain_step():
+            z_s = eng.ae_encode(audio_s)
+            z_t = eng.ae_encode(audio_t)  # noqa: F841  (timbre branch: ECAPA is a SURVEY 8f 'next' row; cond is supplied)
+            tcond = eng.structure_encode(z_s) if se_sd is not None else tc
+            z = eng.sample(x0, cond, tcond, NS, 2.0, 1.0)
+            return eng.ae_decode(z)
+
+        chain_step()
+        chain_ms, _ = timed(chain_step, args.steps)
+        rtf = {"value": B * world * (CHUNK / SR) * args.steps / (chain_ms / 1e3), "unit": "x real time",
+               "ms_per_chunk_batch": chain_ms / args.steps,
+               "chain": "2x AutoEncoder.encode + Encoder1D + sample(50 steps, CFG) + AutoEncoder.decode; timbre vector supplied"}
+
+    # ---- roofline of the dominant kernel (tcgen05 tap-GEMM), per-launch CUDA events on the launching stream ----------
+    pk = peaks()
+    roof = None
+    prof = None
+    if rank == 0:
+        eng.profile(True)
+        eng.sample(x0, cond, tc, NS, 2.0, 1.0)
+        prof = eng.profile_read()
+        eng.profile(False)
+        g = prof["tap_gemm_tc" if args.precision != "fp32_simt" else "tap_gemm_simt"]
+        tot_prof = sum(v["ms"] for v in prof.values())
+        if g["launches"]:
+            ach = g["flops"] / (g["ms"] / 1e3) / 1e12
+            issued = 3 if args.precision == "fp32" else 1
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": "tap_gemm_tc_kernel",
+                    "launches_per_sample": g["launches"], "avg_launch_us": g["ms"] * 1e3 / g["launches"],
+                    "flops_per_launch": g["flops"] / g["launches"], "share_of_profiled_ms": g["ms"] / tot_prof,
+                    "issued_mma_per_product": issued, "issued_frac": ach * issued / pk["bf16_sustained"],
+                    "peak_source": pk["source"] + ", bf16 sustained"}
+            tr = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr):
+                with open(tr) as fh:
+                    roof["traffic"] = json.load(fh).get("tap_gemm_tc_kernel_bytes_per_launch")
+
+    # ---- CPU baseline: the oracle port of the reference sampler on this box's host cores (rank 0, N = 1 only) --------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_steps = 3
+        v, cores, secs = cpu_reference_steps_per_s(args.model, B, cpu_steps)
+        cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"{cpu_steps} of {NS} diffusion steps, B={B}, T=256 ({secs:.1f} s of CPU work)"}
+
+    if rank == 0:
+        dtype = {"fp32": "fp32 (bf16x3 split products on tcgen05, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)",
+                 "fp32_simt": "fp32 (FFMA)"}[args.precision]
+        line = {
+            "metric": "diffusion-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": f"{args.model} audio-to-audio, batch={B}/GPU, {NS} Euler steps x 3-way CFG, 524288-sample chunk (T=256)",
+                       "batch_per_gpu": B, "global_batch": B * world, "nb_steps": NS, "frames": 256, "precision": args.precision,
+                       "parallelism": f"batch-shard x{world}, one all_gather of the latents" if world > 1 else "single GPU",
+                       "l2": "flushed (256 MiB write) before every timed step; per-step CUDA events",
+                       "one_bench_step": f"one RectifiedFlow.sample call = {NS} diffusion steps over {B} streams (x3 CFG rows)"},
+            "sequence_steps_per_s": value * B,
+            "algorithmic_tflops": 3 * B * FLOP_PER_SEQ[args.model] * NS * args.steps * world / (total_ms / 1e3) / 1e12,
+            "e2e": e2e, "rtf": rtf, "roofline": roof, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
+            "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in (prof or {}).items()},
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,21 @@ int64_t after_launch_count(after_handle h);
 int64_t after_device_bytes(after_handle h);
 int after_ae_ratio(after_handle h);
 
+/* Per-kernel-class device timing for roofline reports (no reference counterpart: the reference has no
+ * profiler).  While enabled every launch of the profiled classes is bracketed by CUDA
+ * events on the library's work stream and CUDA-graph replay is bypassed, so the same kernels run one by one.
+ * after_profile_read synchronises the device and returns, for one class, the number of launches since
+ * after_profile_enable(h, 1), their summed duration (ms) and their summed algorithmic flops / bytes. */
+#define AFTER_KERNEL_TAP_GEMM_TC 0   /* tcgen05 tap-GEMM (linears + convolutions) */
+#define AFTER_KERNEL_TAP_GEMM_SIMT 1 /* fp32 FFMA tap-GEMM */
+#define AFTER_KERNEL_ATTENTION 2     /* banded attention + residual + AdaLN-c + LN3 */
+#define AFTER_KERNEL_ROW_NORM 3      /* AdaLN-t + LN1 */
+#define AFTER_KERNEL_ACT_OPERAND 4   /* GroupNorm/BatchNorm + Snake/SiLU operand pass */
+#define AFTER_KERNEL_PQMF 5          /* PQMF analysis / synthesis */
+int after_profile_enable(after_handle h, int on);
+int after_profile_read(after_handle h, int kernel_class, int64_t* launches, double* ms, double* flops,
+                       double* bytes);
+
 /* Unit-level entry point used by the parity tests of the tensor-core GEMM:
  * C[M,N] = A[M,K] * W[N,K]^T (+bias[N]) in the given precision; all dev fp32. */
 int after_debug_gemm(after_handle h, const float* A, const float* W, const float* bias, float* C,
