@@ -112,6 +112,15 @@ def cpu_reference_steps_per_s(name, B, nb_steps, repeats=1, threads=None):
     return nb_steps / best, threads, best
 
 
+def workload_config(args, world):
+    B, NS = args.batch, args.nb_steps
+    return {"workload": f"{args.model} audio-to-audio, batch={B}/GPU, {NS} Euler steps x 3-way CFG, 524288-sample chunk (T=256)",
+            "batch_per_gpu": B, "global_batch": B * world, "nb_steps": NS, "frames": 256, "precision": args.precision,
+            "parallelism": f"batch-shard x{world}, one all_gather of the latents" if world > 1 else "single GPU",
+            "l2": "flushed (256 MiB write) before every timed step; per-step CUDA events",
+            "one_bench_step": f"one RectifiedFlow.sample call = {NS} diffusion steps over {B} streams (x3 CFG rows)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,8 +145,7 @@ def run_reference(args):
         "impl": "reference", "metric": "diffusion-steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * args.nb_steps / sample_steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"{args.model} audio-to-audio sampler, batch={args.batch}, {args.nb_steps} steps, T=256, CPU",
-                   "batch_per_gpu": args.batch, "nb_steps": args.nb_steps},
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,8 +192,8 @@ def main():
 
     B, NS = args.batch, args.nb_steps
     mc, x0_all, cond_all, tc_all = synth_setup(args.model, B * world)  # host-generated once: identical for any N
-    sl = slice(rank * B, (rank + 1) * B)
-    x0_h, cond_h, tc_h = (t[sl].contiguous().pin_memory() for t in (x0_all, cond_all, tc_all))
+    from after_b200 import parallel
+    x0_h, cond_h, tc_h = (t.pin_memory() for t in parallel.shard([x0_all, cond_all, tc_all], world, rank))
     acfg = config.base_autoencoder()
     den_sd = synth.denoiser_state_dict(mc.denoiser, 0)
     chain = not args.no_chain
@@ -195,13 +203,10 @@ def main():
                  structure_state=se_sd, precision=args.precision, device=local, max_batch=B, max_steps=NS, max_samples=CHUNK)
     x0, cond, tc = x0_h.to(dev), cond_h.to(dev), tc_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = torch.empty(world * B, x0.shape[1], x0.shape[2], device=dev) if world > 1 else None
 
     def one_step():
         out = eng.sample(x0, cond, tc, NS, 2.0, 1.0)
-        if world > 1:  # the single collective of the path: gather the generated latents
-            dist.all_gather_into_tensor(gathered, out)
-        return out
+        return parallel.gather_streams(out, B * world)  # the single collective of the path (no-op at N = 1)
 
     for _ in range(args.warmup):
         one_step()
@@ -295,7 +300,8 @@ def main():
     # ---- CPU baseline: the oracle port of the reference sampler on this box's host cores (rank 0, N = 1 only) --------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_steps = 3
+        v0, cores, _ = cpu_reference_steps_per_s(args.model, B, 2)          # probe, then ~12 s of CPU work
+        cpu_steps = int(max(3, min(NS, round(12.0 * v0))))
         v, cores, secs = cpu_reference_steps_per_s(args.model, B, cpu_steps)
         cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                "sample": f"{cpu_steps} of {NS} diffusion steps, B={B}, T=256 ({secs:.1f} s of CPU work)"}
@@ -307,11 +313,7 @@ def main():
             "metric": "diffusion-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": f"{args.model} audio-to-audio, batch={B}/GPU, {NS} Euler steps x 3-way CFG, 524288-sample chunk (T=256)",
-                       "batch_per_gpu": B, "global_batch": B * world, "nb_steps": NS, "frames": 256, "precision": args.precision,
-                       "parallelism": f"batch-shard x{world}, one all_gather of the latents" if world > 1 else "single GPU",
-                       "l2": "flushed (256 MiB write) before every timed step; per-step CUDA events",
-                       "one_bench_step": f"one RectifiedFlow.sample call = {NS} diffusion steps over {B} streams (x3 CFG rows)"},
+            "config": workload_config(args, world),
             "sequence_steps_per_s": value * B,
             "algorithmic_tflops": 3 * B * FLOP_PER_SEQ[args.model] * NS * args.steps * world / (total_ms / 1e3) / 1e12,
             "e2e": e2e, "rtf": rtf, "roofline": roof, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
