@@ -128,6 +128,7 @@ int after_create(const after_config* cfg, int device, after_handle* out) {
     h->device = device;
     DeviceGuard g(device);
     h->bridge.init();
+    tc_init_kernels();
     *out = h.release();
     return AFTER_OK;
   } catch (const Error& e) {

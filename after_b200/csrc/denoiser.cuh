@@ -235,9 +235,16 @@ struct Denoiser {
     // q,k,v read once + h read/write + operand write; ~2 * keys * 64 * 2 flops per (token, head)
     ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
-    attn_adaln_c_ln3_kernel<NH, MAXK><<<ceil_div(rows, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
-                                                                         layers[l].n3_g, layers[l].n3_b, rows, T,
-                                                                         cfg.attention_chunk_size, cfg.local_attention_size);
+    if (cfg.attention_chunk_size == 4) {
+      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
+      attn_chunk4_kernel<NH, MAXK><<<ceil_div(chunks, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
+                                                                        layers[l].n3_g, layers[l].n3_b, n_seq, T,
+                                                                        cfg.local_attention_size);
+    } else {
+      attn_adaln_c_ln3_kernel<NH, MAXK><<<ceil_div(rows, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
+                                                                           layers[l].n3_g, layers[l].n3_b, rows, T,
+                                                                           cfg.attention_chunk_size, cfg.local_attention_size);
+    }
     AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
   }
   void attn(int l, const float* adaC_step, int rows, int T, cudaStream_t st) {

@@ -54,6 +54,8 @@ struct GemmEpi {
   int stat_groups = 0;
   int stat_cpg = 1;                  // channels per group
   int stat_cmod = 0;                 // channel = n % stat_cmod (transposed conv: several phases share channels)
+  int debug_skip = 0;                // profiling experiments only: 1 = drop the epilogue's global traffic
+  unsigned long long* debug_ts = nullptr;  // profiling experiments only: %globaltimer marks of CTA 0
 };
 
 // vals: NV consecutive columns [col0, col0+NV) of frame t of batch b; col0 % 4 == 0, NV % 4 == 0.
@@ -314,6 +316,148 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split form: issue now, wait later (tcgen05.wait::ld covers every outstanding load of the warp)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Row-coalesced epilogue of one 32 (frames) x 32 (columns) accumulator block.  On entry lane l holds row l of the
+// block in v[32] (the TMEM 32x32b layout); the block is transposed through a per-warp shared-memory tile so that
+// afterwards lane l owns COLUMN l and the warp walks the rows: every global access (residual, fp32 / bf16 outputs,
+// RoPE table) is then one contiguous 128-byte (64-byte for bf16) row segment.  Frames >= T are skipped (uniform).
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per warp; 16-byte chunks XOR-swizzled by (row & 7): conflict-free both ways
+constexpr int EPI_WARPS = 8;                  // warps 2..9: TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2
+
+// Epilogue flavours of the pair kernel, resolved at compile time so that each instantiation carries only its own code:
+//   EPI_PLAIN : (+bias) (+residual) -> fp32 (and/or bf16 hi/lo), optional GroupNorm statistics
+//   EPI_ROPE  : rotary embedding on the q / k thirds -> fp32                       (QKV projection, no bias)
+//   EPI_GELU  : +bias, exact GELU -> bf16 hi/lo (and/or fp32)                      (MLP up-projection)
+enum EpiMode { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_GELU = 2 };
+
+// Global operands of one block's epilogue (residual rows or RoPE cos/sin rows), requested before the TMEM load.
+struct EpiAux {
+  float4 a[8];
+};
+template <int MODE>
+__device__ __forceinline__ void epi_prefetch(const GemmEpi& e, EpiAux& aux, int b, int t_base, int T, int col0, int lane) {
+  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  const int col = col0 + c4;
+  const int nvalid = T - t_base;
+  if (MODE == EPI_PLAIN) {
+    if (e.res) {
+      const float* p = e.res + ((size_t)b * T + t_base + rsub) * e.ldo + col;
+      const size_t step = (size_t)4 * e.ldo;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        aux.a[i] = (i * 4 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        p += step;
+      }
+    }
+  } else if (MODE == EPI_ROPE) {
+    const bool rot = (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
+    if (rot) {
+      const float2* p = e.rope_tab + (size_t)(t_base + rsub) * e.rot_half + ((col & 63) >> 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        aux.a[i] = (i * 4 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(1.f, 0.f, 1.f, 0.f);
+        p += 4 * e.rot_half;
+      }
+    }
+  }
+}
+
+// Row-coalesced epilogue of one 32 (frames) x 32 (columns) accumulator block.  On entry lane l holds row l of the
+// block in v[32] (the TMEM 32x32b layout); the block is transposed through a per-warp XOR-swizzled shared-memory
+// tile so that afterwards lane l owns 4 consecutive COLUMNS (l & 7) * 4 of rows (l >> 3) + 4 i: every global access
+// (residual, fp32 / bf16 outputs, RoPE table) is then a contiguous 128-byte (64-byte for bf16) row segment.
+template <int MODE>
+__device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const uint32_t* v, const EpiAux& aux, float4 bias4, int b,
+                                          int t_base, int T, int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+  const int c4 = (lane & 7) * 4;
+  const int rsub = lane >> 3;
+  const int col = col0 + c4;
+  const int nvalid = T - t_base;
+  const bool rot = MODE == EPI_ROPE && (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
+  const bool has_res = MODE == EPI_PLAIN && e.res != nullptr;
+  const size_t off0 = ((size_t)b * T + t_base + rsub) * e.ldo + col;
+  const size_t step = (size_t)4 * e.ldo;
+  float* pf = e.out_f32 ? e.out_f32 + off0 : nullptr;
+  __nv_bfloat16* ph = e.out_hi ? e.out_hi + off0 : nullptr;
+  __nv_bfloat16* pl = e.out_lo ? e.out_lo + off0 : nullptr;
+  float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+    x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+    if (MODE == EPI_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+    if (rot) {
+      const float4 cs = aux.a[i];
+      const float a0 = x.x, b0 = x.y, a1 = x.z, b1 = x.w;
+      x.x = a0 * cs.x - b0 * cs.y; x.y = b0 * cs.x + a0 * cs.y;
+      x.z = a1 * cs.z - b1 * cs.w; x.w = b1 * cs.z + a1 * cs.w;
+    }
+    if (has_res) { x.x += aux.a[i].x; x.y += aux.a[i].y; x.z += aux.a[i].z; x.w += aux.a[i].w; }
+    if (r < nvalid && !(e.debug_skip & 1)) {
+      if (MODE == EPI_PLAIN) {
+        ssum += (x.x + x.y) + (x.z + x.w);
+        ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
+      }
+      if (pf) *reinterpret_cast<float4*>(pf) = x;
+      if (ph) {
+        __nv_bfloat16 hh[4], ll[4];
+        split_bf16(x.x, hh[0], ll[0]); split_bf16(x.y, hh[1], ll[1]); split_bf16(x.z, hh[2], ll[2]); split_bf16(x.w, hh[3], ll[3]);
+        *reinterpret_cast<uint2*>(ph) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+        if (pl) *reinterpret_cast<uint2*>(pl) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+      }
+    }
+    if (pf) pf += step;
+    if (ph) ph += step;
+    if (pl) pl += step;
+  }
+  if (MODE == EPI_PLAIN && e.stats) {
+    // fold the 4 row sub-lanes (xor 8, 16) and the neighbouring 4-column lane (xor 1): lanes 0,2,4,6 then hold the
+    // sums of 8 aligned columns, which always share a GroupNorm group here (channels per group % 8 == 0)
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);  ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);  ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+    if ((lane & 0x19) == 0) {
+      const int c = e.stat_cmod > 0 ? col % e.stat_cmod : col;
+      double* p = e.stats + ((size_t)b * e.stat_groups + c / e.stat_cpg) * 2;
+      atomicAdd(p, (double)ssum);
+      atomicAdd(p + 1, (double)ssq);
+    }
+  }
+  __syncwarp();
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -459,6 +603,269 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN < 32 ? 32 : BN) : "memory");
   }
+}
+
+
+// =====================================================================================
+// tcgen05 tap-GEMM, CTA-pair version (cta_group::2): the main kernel.
+//
+// A cluster of two CTAs (one TPC) owns a 256 x BN output tile: CTA r holds frames [t0 + 128 r, +128) of A and
+// rows [n0 + r BN/2, +BN/2) of W in its own shared memory, the leader CTA issues one M=256 MMA per K=16 slice and
+// each CTA receives its 128 x BN half of the accumulator in its own TMEM.  Halving the W bytes each SM pulls from
+// L2 is what matters: the 1-CTA 128x128 kernel needs ~85 B/clk/SM of operands (bf16x3 mode) against the ~42 B/clk/SM
+// the L2 delivers chip-wide, this one needs ~43.
+//
+// Persistent: grid = 2 x min(#tiles, #SM pairs); each cluster walks tiles (n fastest) round-robin.  The TMEM
+// accumulator is double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0 : TMA producer (both CTAs; transaction bytes of both land on the leader's `full` barrier)
+//   warp 1 : TMEM alloc/dealloc (both CTAs), MMA issue (leader only; tcgen05.commit multicast frees the stage in
+//            both CTAs and publishes the accumulator to both epilogues)
+//   warps 2-5 : epilogue (tcgen05.ld -> epi_store); their arrival on the leader's `tmem_empty` recycles the buffer
+// =====================================================================================
+__device__ __forceinline__ void ts_mark(const GemmEpi& e, int slot) {
+  if (e.debug_ts && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    e.debug_ts[slot] = t;
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint32_t mbar_cluster, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint32_t mbar_cluster, void* dst, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(int n) {  // M = 256 across the CTA pair
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+struct Smem2 {
+  static constexpr int A_BYTES = BM * BK * 2;         // 16 KiB: this CTA's 128 frames
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the W tile
+  __host__ __device__ static constexpr int stage_bytes(int nprod) { return (nprod > 1 ? 2 : 1) * (A_BYTES + B_BYTES); }
+  __host__ __device__ static constexpr int stages(int nprod) {
+    int s = (192 * 1024) / stage_bytes(nprod);
+    return s > 8 ? 8 : s;
+  }
+  __host__ __device__ static constexpr int total(int nprod) { return stages(nprod) * stage_bytes(nprod) + 1024 + 512 + EPI_WARPS * EPI_STAGE_BYTES; }
+};
+
+constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS;
+
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    GemmEpi epi, const __grid_constant__ TapTable taps, int T, int Cin, int nprod, int n_tiles_n,
+                    int m_tiles_per_b, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int A_BYTES = Smem2<BN>::A_BYTES, B_BYTES = Smem2<BN>::B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  const int n_ops = nprod > 1 ? 2 : 1;
+  const int stage_bytes = n_ops * (A_BYTES + B_BYTES);
+  const int n_stages = nprod > 1 ? Smem2<BN>::stages(3) : Smem2<BN>::stages(1);
+
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)n_stages * stage_bytes);
+  uint64_t* full = bars;             // [8]  (the leader's copies are the live ones)
+  uint64_t* empty = bars + 8;        // [8]
+  uint64_t* tmem_full = bars + 16;   // [2]
+  uint64_t* tmem_empty = bars + 18;  // [2]  (leader's copies)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* epi_stage = reinterpret_cast<float*>(bars + 64);  // EPI_WARPS x [32][32], swizzled
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) ts_mark(epi, 0);
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int cblocks = Cin / BK;
+  const int nkb = taps.ntaps * cblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    if (nprod > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);  // epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ts_mark(epi, 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int nt = tile % n_tiles_n, mt = tile / n_tiles_n;
+        const int b = mt / m_tiles_per_b;
+        const int t0 = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM;
+        const int n0 = nt * BN;
+        const int oph = taps.n_per_phase > 0 ? n0 / taps.n_per_phase : 0;
+        const int nrow = n0 + (int)rank * (BN / 2);
+        for (int tap = 0; tap < taps.ntaps; ++tap) {
+          const int ta = t0 + taps.shift[oph][tap];
+          const int ph = taps.phase[oph][tap];
+          for (int cb = 0; cb < cblocks; ++cb, ++it) {
+            const int s = it % n_stages;
+            const uint32_t par = (it / n_stages) & 1;
+            mbar_wait(&empty[s], par ^ 1);
+            uint8_t* st = tiles + (size_t)s * stage_bytes;
+            const uint32_t fb = mapa(smem_u32(&full[s]), 0);
+            if (epi.debug_skip & 2) {  // experiment: no operand traffic at all
+              if (rank == 0) mbar_expect_tx(&full[s], 0);
+              continue;
+            }
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
+            const int kcol = (tap * cblocks + cb) * BK;
+            tma2_load_4d(&tmA_hi, fb, st, cb * BK, ph, ta, b);
+            tma2_load_2d(&tmB_hi, fb, st + A_BYTES, kcol, nrow);
+            if (nprod > 1) {
+              tma2_load_4d(&tmA_lo, fb, st + A_BYTES + B_BYTES, cb * BK, ph, ta, b);
+              tma2_load_2d(&tmB_lo, fb, st + 2 * A_BYTES + B_BYTES, kcol, nrow);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc2(BN);
+      int it = 0, ti = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t par = (it / n_stages) & 1;
+          mbar_wait(&full[s], par);
+          if (it < 4) ts_mark(epi, 2 + it);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
+          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + A_BYTES);
+          const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+          uint32_t accum = kb > 0;
+          if (epi.debug_skip & 4) {  // experiment: no MMAs
+            umma2_commit_mc(&empty[s]);
+            continue;
+          }
+          if (nprod > 1) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) { umma2_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accum); accum = 1; }
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma2_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) { umma2_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accum); accum = 1; }
+          umma2_commit_mc(&empty[s]);
+        }
+        umma2_commit_mc(&tmem_full[buf]);
+        if (ti < 4) ts_mark(epi, 8 + ti);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const uint32_t te0 = mapa(smem_u32(&tmem_empty[0]), 0), te1 = mapa(smem_u32(&tmem_empty[1]), 0);
+    int ti = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      const int nt = tile % n_tiles_n, mt = tile / n_tiles_n;
+      const int b = mt / m_tiles_per_b;
+      const int t_base = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM + quad * 32;
+      const int n0 = nt * BN;
+      const int buf = ti & 1;
+      mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+      if (warp == 2 && lane == 0 && ti < 4) ts_mark(epi, 12 + 2 * ti);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      float* stg = epi_stage + (warp - 2) * (32 * 32);
+      if (t_base < T) {
+        constexpr int HALF = BN / 2;  // this warp's column range: [chalf * HALF, +HALF)
+        const int cbeg = ((warp - 2) >> 2) * HALF;
+#pragma unroll 1
+        for (int c = cbeg; c < cbeg + HALF; c += 32) {
+          EpiAux aux;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(epi.debug_skip & 1)) {
+            epi_prefetch<MODE>(epi, aux, b, t_base, T, n0 + c, lane);  // in flight during the TMEM load
+            if (epi.bias) bias4 = *reinterpret_cast<const float4*>(epi.bias + n0 + c + (lane & 7) * 4);
+          }
+          uint32_t v[32];
+          tmem_ld32_issue(taddr + c, v);
+          tmem_ld_wait();
+          epi_block<MODE>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (warp == 2 && lane == 0 && ti < 4) ts_mark(epi, 13 + 2 * ti);
+      if (lane == 0) mbar_arrive_cluster(buf ? te1 : te0);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) ts_mark(epi, 20);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+  if (threadIdx.x == 32) ts_mark(epi, 21);
 }
 
 }  // namespace tc

@@ -71,7 +71,25 @@ struct GemmWeight {
   int N = 0, K = 0, Cin = 0, bn = 0;
   TapTable taps;
   bool tc_ok = false;
+  // CTA-pair kernel: 256 x bn2 tiles, each CTA loads bn2/2 rows of W
+  CUtensorMap map2_hi{}, map2_lo{};
+  int bn2 = 0;
+  bool tc2_ok = false;
 };
+
+inline int pick_bn2(int N, int n_per_phase) {
+  for (int bn : {256, 128, 64})
+    if (N % bn == 0 && (n_per_phase == 0 || n_per_phase % bn == 0)) return bn;
+  return 0;
+}
+inline bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AFTER_GEMM");
+    v = (e && std::string(e) == "1cta") ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // A GEMM A-operand buffer: fp32 (SIMT modes) or bf16 hi/lo (tcgen05 modes); the 4-D maps depend on the view
 // (C, P, T, B) and are cached per view.
@@ -130,6 +148,12 @@ inline void build_gemm_weight(GemmWeight& gw, Arena& arena, const std::vector<fl
     AFTER_CUDA_CHECK(cudaGetLastError());
     gw.map_hi = make_tmap_weight(gw.hi, N, gw.K, gw.bn);
     gw.map_lo = make_tmap_weight(gw.lo, N, gw.K, gw.bn);
+    gw.bn2 = pick_bn2(N, taps.n_per_phase);
+    gw.tc2_ok = gw.bn2 > 0;
+    if (gw.tc2_ok) {
+      gw.map2_hi = make_tmap_weight(gw.hi, N, gw.K, gw.bn2 / 2);
+      gw.map2_lo = make_tmap_weight(gw.lo, N, gw.K, gw.bn2 / 2);
+    }
   }
 }
 
@@ -157,6 +181,51 @@ inline void launch_tap_gemm_tc_bn(const ActOperand::Maps& am, const GemmWeight& 
   AFTER_CUDA_CHECK(cudaGetLastError());
 }
 
+template <int BN, int MODE>
+inline void launch_tap_gemm_tc2_bn(const ActOperand::Maps& am, const GemmWeight& W, const GemmEpi& epi, int B, int T,
+                                   int nprod, cudaStream_t st) {
+  static bool attr_set = false;
+  static int n_pairs = 0;
+  const int smem = tc::Smem2<BN>::total(nprod > 1 ? 3 : 1);
+  if (!attr_set) {
+    const int mx = std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1));
+    AFTER_CUDA_CHECK(cudaFuncSetAttribute(tc::tap_gemm_tc2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    int dev = 0, sms = 0;
+    AFTER_CUDA_CHECK(cudaGetDevice(&dev));
+    AFTER_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    n_pairs = std::max(1, sms / 2);
+    attr_set = true;
+  }
+  const int n_tiles_n = W.N / BN;
+  const int m_tiles_per_b = ceil_div(T, 2 * tc::BM);
+  const int n_tiles = n_tiles_n * m_tiles_per_b * B;
+  const int clusters = std::min(n_tiles, n_pairs);
+  tc::tap_gemm_tc2_kernel<BN, MODE><<<2 * clusters, tc::NUM_THREADS2, smem, st>>>(am.hi, am.lo, W.map2_hi, W.map2_lo, epi, W.taps, T,
+                                                                            W.Cin, nprod, n_tiles_n, m_tiles_per_b, n_tiles);
+  AFTER_CUDA_CHECK(cudaGetLastError());
+}
+
+// cudaFuncSetAttribute must not first run inside a stream capture: touch every instantiation once up front.
+inline void tc_init_kernels() {
+  static bool done = false;
+  if (done) return;
+  auto set = [](const void* f, int bytes) {
+    AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  };
+  set((const void*)tc::tap_gemm_tc_kernel<128>, std::max(tc::Smem<128>::total(3), tc::Smem<128>::total(1)));
+  set((const void*)tc::tap_gemm_tc_kernel<64>, std::max(tc::Smem<64>::total(3), tc::Smem<64>::total(1)));
+  set((const void*)tc::tap_gemm_tc_kernel<32>, std::max(tc::Smem<32>::total(3), tc::Smem<32>::total(1)));
+#define AFTER_SET_TC2(BN)                                                                                          \
+  set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_PLAIN>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1))); \
+  set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_ROPE>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));  \
+  set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_GELU>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));
+  AFTER_SET_TC2(256)
+  AFTER_SET_TC2(128)
+  AFTER_SET_TC2(64)
+#undef AFTER_SET_TC2
+  done = true;
+}
+
 void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int groups, cudaStream_t st);
 
 // Dispatch.  `precision` is the handle's arithmetic mode.  A: the operand (B, T, P, Cin).  The output is
@@ -165,6 +234,11 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
                      cudaStream_t st) {
   const bool tc_mode = precision != AFTER_PRECISION_FP32_SIMT;
   epi.bias = W.bias;
+  {
+    static int skip = -1;
+    if (skip < 0) { const char* e = getenv("AFTER_DEBUG_SKIP_EPILOGUE"); skip = e ? atoi(e) : 0; }
+    epi.debug_skip = skip;
+  }
   // algorithmic work of this launch: 2*M*N*K flops; operand read once + result written once (+ residual read)
   const double rows = (double)B * T;
   const double g_flops = 2.0 * rows * W.N * W.K;
@@ -174,6 +248,23 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
     AFTER_REQUIRE(A.hi != nullptr, AFTER_ESTATE, "operand has no bf16 copy");
     const int nprod = precision == AFTER_PRECISION_BF16 ? 1 : 3;
     const ActOperand::Maps& am = A.maps(W.Cin, P, T, B);
+    const bool flavour_ok = (!epi.rope || (!epi.bias && !epi.res && !epi.gelu && !epi.stats)) &&
+                            (!epi.gelu || (!epi.res && !epi.stats)) && (!epi.stats || epi.stat_cpg % 8 == 0);
+    if (W.tc2_ok && use_pair_kernel() && flavour_ok) {
+      // epilogue flavour (compile-time specialisations; anything a flavour cannot express falls back to the 1-CTA kernel)
+#define AFTER_LAUNCH_TC2(MODE)                                                                  \
+  do {                                                                                          \
+    if (W.bn2 == 256) launch_tap_gemm_tc2_bn<256, MODE>(am, W, epi, B, T, nprod, st);           \
+    else if (W.bn2 == 128) launch_tap_gemm_tc2_bn<128, MODE>(am, W, epi, B, T, nprod, st);      \
+    else launch_tap_gemm_tc2_bn<64, MODE>(am, W, epi, B, T, nprod, st);                         \
+  } while (0)
+      if (epi.rope) AFTER_LAUNCH_TC2(tc::EPI_ROPE);
+      else if (epi.gelu) AFTER_LAUNCH_TC2(tc::EPI_GELU);
+      else AFTER_LAUNCH_TC2(tc::EPI_PLAIN);
+#undef AFTER_LAUNCH_TC2
+      AFTER_COUNT_LAUNCH();
+      return;
+    }
     if (W.bn == 128) launch_tap_gemm_tc_bn<128>(am, W, epi, B, T, nprod, st);
     else if (W.bn == 64) launch_tap_gemm_tc_bn<64>(am, W, epi, B, T, nprod, st);
     else launch_tap_gemm_tc_bn<32>(am, W, epi, B, T, nprod, st);
@@ -229,10 +320,36 @@ inline void debug_gemm(const float* A, const float* W, const float* bias, float*
       gw.map_hi = make_tmap_weight(gw.hi, N, K, gw.bn);
       gw.map_lo = make_tmap_weight(gw.lo, N, K, gw.bn);
       gw.tc_ok = true;
+      gw.bn2 = pick_bn2(N, 0);
+      gw.tc2_ok = gw.bn2 > 0;
+      if (gw.tc2_ok) {
+        gw.map2_hi = make_tmap_weight(gw.hi, N, K, gw.bn2 / 2);
+        gw.map2_lo = make_tmap_weight(gw.lo, N, K, gw.bn2 / 2);
+      }
     }
     GemmEpi e; e.out_f32 = C; e.ldo = N;
+    const char* tr = getenv("AFTER_DEBUG_TRACE");
+    unsigned long long* ts = nullptr;
+    if (tr && tr[0] == '1') {
+      ts = tmp.alloc<unsigned long long>(32);
+      AFTER_CUDA_CHECK(cudaMemsetAsync(ts, 0, 32 * 8, st));
+      e.debug_ts = ts;
+      // run twice so the traced launch is warm
+      GemmEpi e0 = e; e0.debug_ts = nullptr;
+      tap_gemm(a, 1, M, 1, gw, e0, precision, st);
+    }
     tap_gemm(a, 1, M, 1, gw, e, precision, st);
     AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (ts) {
+      unsigned long long h[32];
+      AFTER_CUDA_CHECK(cudaMemcpy(h, ts, sizeof(h), cudaMemcpyDeviceToHost));
+      const char* names[22] = {"entry", "prologue_done", "full0", "full1", "full2", "full3", "", "", "tile0_issued", "tile1_issued",
+                               "tile2_issued", "tile3_issued", "epi0_begin", "epi0_end", "epi1_begin", "epi1_end", "epi2_begin",
+                               "epi2_end", "epi3_begin", "epi3_end", "teardown_sync", "dealloc_done"};
+      fprintf(stderr, "trace M=%d N=%d K=%d prec=%d (ns since kernel entry of CTA 0):\n", M, N, K, precision);
+      for (int i = 0; i < 22; ++i)
+        if (h[i]) fprintf(stderr, "  %-14s %8lld\n", names[i], (long long)(h[i] - h[0]));
+    }
   } catch (...) {
     cudaStreamSynchronize(st);
     tmp.release();

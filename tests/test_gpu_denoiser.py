@@ -94,7 +94,7 @@ def test_model_forward_and_sample_match_reference(golden, name, precision):
 def test_sample_matches_oracle(name, variant, clamp):
     """Fresh seeded inputs, ragged frame count, both CFG layouts; checker = CPU oracle."""
     from oracle import after_oracle as O
-    frames, B, steps = 44, 3, 3
+    frames, B, steps = 46, 3, 3  # 46 % 4 != 0: ragged last attention chunk
     eng, sd, mc = make_engine(name, 77, "fp32", frames)
     try:
         x0, cond, tc = synth.synth_inputs(B, mc.denoiser, seed=5, frames=frames)
