@@ -47,6 +47,20 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// erf-form GELU with erf from Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 rounding level), branch
+// free: ~14 instructions instead of erff's ~35 with divergent ranges.  Used in the tensor-core GEMM epilogue, where
+// the 9.4 M activations per MLP up-projection are evaluated by only 8 warps per SM.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * __expf(-z * z);
+  const float erf_x = copysignf(1.0f - erfc_z, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));

@@ -237,7 +237,7 @@ struct Denoiser {
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
     if (cfg.attention_chunk_size == 4) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      attn_chunk4_kernel<NH, MAXK><<<ceil_div(chunks, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
+      attn_chunk4_kernel<NH, MAXK><<<chunks, NH * 32, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
                                                                         layers[l].n3_g, layers[l].n3_b, n_seq, T,
                                                                         cfg.local_attention_size);
     } else {
@@ -264,8 +264,8 @@ struct Denoiser {
   void run_network(const float* x_src, int n_src, int N, int T, const float* adaC_step, cudaStream_t st) {
     const int rows = N * T;
     {
-      dim3 grid(ceil_div(T, 32), n_src);
-      patch_embed_kernel<32><<<grid, 256, C * 32 * sizeof(float), st>>>(x_src, pe_wt, pe_b, h0, C, T, D);
+      dim3 grid(ceil_div(T, 4), n_src);
+      patch_embed_kernel<4><<<grid, 256, C * 4 * sizeof(float), st>>>(x_src, pe_wt, pe_b, h0, C, T, D);
       AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
     }
     for (int l = 0; l < L; ++l) {

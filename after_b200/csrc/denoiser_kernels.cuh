@@ -114,36 +114,38 @@ adaln_t_ln1_kernel(const float* h_in, float* h_out, RowOperandOut a_out,
 // Requires chunk == 4 (every shipped config; other chunk sizes take the one-warp-per-token kernel below).
 // -------------------------------------------------------------------------------------------
 template <int NH, int MAXK>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(NH * 32, 32 / NH)
 attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
                    const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
                    const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window) {
+  // Block = one attention chunk (4 queries), warp = head: NH warps x 1536 chunks keeps ~64 warps resident per SM, which
+  // is what hides the L2 round trips of the key/value rows (the kernel is latency-, not bandwidth-bound).
+  // Phase 1 (all warps): lane = (query qi = lane >> 3, dsub = lane & 7) owns dims [4 dsub, +4) and [32 + 4 dsub, +4) of
+  // this warp's head; scores are reduced over the 8 lanes of a query with 3 shuffles; h + softmax.V goes to smem.
+  // Phase 2 (warps 0..3): one query row each: LayerNorm -> AdaLN-c -> h ; LayerNorm(affine) -> next GEMM's operand.
   constexpr int D = NH * 64;
+  constexpr int NV = D / 32;
+  __shared__ __align__(16) float xs[4][D];
   const int chunks_per_seq = (T + 3) >> 2;
-  const int cid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (cid >= n_seq * chunks_per_seq) return;
-  const int lane = threadIdx.x & 31;
-  const int qi = lane >> 3, dsub = lane & 7;
-  const int n = cid / chunks_per_seq;
-  const int c0 = (cid - n * chunks_per_seq) * 4;
-  const int ce = min(c0 + 4, T);
-  const int t = min(c0 + qi, T - 1);            // ragged last chunk: surplus query groups recompute the last row
-  const bool live = c0 + qi < T;
-  const int ks0 = max(0, c0 - window + 1);       // first key any query of the chunk may see (query c0)
-  const int ks = min(c0, max(0, t - window + 1));
-  const int nk = ce - ks0;                       // <= MAXK
-  const int skip = ks - ks0;                     // keys [ks0, ks) are outside this query's window
-  const size_t row = (size_t)n * T + t;
-  // per head a lane owns dims [4 dsub, +4) and [32 + 4 dsub, +4): every row access is two 128-byte segments
-  const float* qrow = qkv + row * (3 * D) + dsub * 4;
-  const float* kbase = qkv + ((size_t)n * T + ks0) * (3 * D) + D + dsub * 4;
-  const float* vbase = kbase + D;
-
-  float x[NH][8];
-#pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    float4 q0 = *reinterpret_cast<const float4*>(qrow + hd * 64);
-    float4 q1 = *reinterpret_cast<const float4*>(qrow + hd * 64 + 32);
+  const int n = blockIdx.x / chunks_per_seq;
+  const int c0 = (blockIdx.x - n * chunks_per_seq) * 4;
+  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int qi = lane >> 3, dsub = lane & 7;
+    const int ce = min(c0 + 4, T);
+    const int t = min(c0 + qi, T - 1);            // ragged last chunk: surplus query groups recompute the last row
+    const int ks0 = max(0, c0 - window + 1);       // first key any query of the chunk may see (query c0)
+    const int ks = min(c0, max(0, t - window + 1));
+    const int nk = ce - ks0;                       // <= MAXK
+    const int skip = ks - ks0;                     // keys [ks0, ks) are outside this query's window
+    const size_t row = (size_t)n * T + t;
+    const float* qrow = qkv + row * (3 * D) + hd * 64 + dsub * 4;
+    const float* kbase = qkv + ((size_t)n * T + ks0) * (3 * D) + D + hd * 64 + dsub * 4;
+    const float* vbase = kbase + D;
+    float4 q0 = *reinterpret_cast<const float4*>(qrow);
+    float4 q1 = *reinterpret_cast<const float4*>(qrow + 32);
+    const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
+    const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
     q0.x *= 0.125f; q0.y *= 0.125f; q0.z *= 0.125f; q0.w *= 0.125f;  // 1/sqrt(64): exact power of two
     q1.x *= 0.125f; q1.y *= 0.125f; q1.z *= 0.125f; q1.w *= 0.125f;
     float s[MAXK];
@@ -151,8 +153,8 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
     for (int j = 0; j < MAXK; ++j) {
       s[j] = 0.f;
       if (j < nk) {
-        const float4 k0 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D) + hd * 64);
-        const float4 k1 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D) + hd * 64 + 32);
+        const float4 k0 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D));
+        const float4 k1 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D) + 32);
         s[j] = (q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w) + (q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w);
       }
     }
@@ -174,73 +176,53 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
       if (j < nk) {
         const float p = expf(s[j] - m);  // exp(-inf) = 0 for masked keys
         l += p;
-        const float4 v0 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D) + hd * 64);
-        const float4 v1 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D) + hd * 64 + 32);
+        const float4 v0 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D));
+        const float4 v1 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D) + 32);
         o[0] = fmaf(p, v0.x, o[0]); o[1] = fmaf(p, v0.y, o[1]); o[2] = fmaf(p, v0.z, o[2]); o[3] = fmaf(p, v0.w, o[3]);
         o[4] = fmaf(p, v1.x, o[4]); o[5] = fmaf(p, v1.y, o[5]); o[6] = fmaf(p, v1.z, o[6]); o[7] = fmaf(p, v1.w, o[7]);
       }
     }
     const float inv = 1.0f / l;
-    const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
-    const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
-    x[hd][0] = fmaf(o[0], inv, r0.x); x[hd][1] = fmaf(o[1], inv, r0.y); x[hd][2] = fmaf(o[2], inv, r0.z); x[hd][3] = fmaf(o[3], inv, r0.w);
-    x[hd][4] = fmaf(o[4], inv, r1.x); x[hd][5] = fmaf(o[5], inv, r1.y); x[hd][6] = fmaf(o[6], inv, r1.z); x[hd][7] = fmaf(o[7], inv, r1.w);
+    float* xp = &xs[qi][hd * 64 + dsub * 4];
+    *reinterpret_cast<float4*>(xp) = make_float4(fmaf(o[0], inv, r0.x), fmaf(o[1], inv, r0.y), fmaf(o[2], inv, r0.z), fmaf(o[3], inv, r0.w));
+    *reinterpret_cast<float4*>(xp + 32) = make_float4(fmaf(o[4], inv, r1.x), fmaf(o[5], inv, r1.y), fmaf(o[6], inv, r1.z), fmaf(o[7], inv, r1.w));
   }
-  // row statistics over the 8 lanes of this query group (biased variance, eps inside the sqrt)
-  auto group_sum = [](float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    return v;
-  };
-  auto stats = [&](float& mean, float& rstd) {
-    float sm = 0.f;
+  __syncthreads();
+  const int qi = hd;  // phase 2: warp w normalises query row w
+  if (qi >= 4 || c0 + qi >= T) return;
+  const size_t row = (size_t)n * T + c0 + qi;
+  float x[NV];
 #pragma unroll
-    for (int hd = 0; hd < NH; ++hd)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sm += x[hd][i];
-    mean = group_sum(sm) / (float)D;
-    float qq = 0.f;
-#pragma unroll
-    for (int hd = 0; hd < NH; ++hd)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = x[hd][i] - mean; qq = fmaf(d, d, qq); }
-    rstd = 1.0f / sqrtf(group_sum(qq) / (float)D + 1e-5f);
-  };
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(&xs[qi][(i * 32 + lane) * 4]);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
   float mean, rstd;
-  stats(mean, rstd);
-  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off + dsub * 4;
+  row_stats<NV>(x, D, mean, rstd);
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
 #pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    const int e = hd * 64;
-    const float4 al0 = *reinterpret_cast<const float4*>(ap + e), al1 = *reinterpret_cast<const float4*>(ap + e + 32);
-    const float4 be0 = *reinterpret_cast<const float4*>(ap + D + e), be1 = *reinterpret_cast<const float4*>(ap + D + e + 32);
-    const float al[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
-    const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[hd][i] = (x[hd][i] - mean) * rstd * (1.f + al[i]) + be[i];
-    if (live) {
-      float* hp = h + row * D + e + dsub * 4;
-      *reinterpret_cast<float4*>(hp) = make_float4(x[hd][0], x[hd][1], x[hd][2], x[hd][3]);
-      *reinterpret_cast<float4*>(hp + 32) = make_float4(x[hd][4], x[hd][5], x[hd][6], x[hd][7]);
-    }
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 al = *reinterpret_cast<const float4*>(ap + e);
+    const float4 be = *reinterpret_cast<const float4*>(ap + D + e);
+    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
+    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
+    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
+    *reinterpret_cast<float4*>(h + row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
   }
-  stats(mean, rstd);
+  row_stats<NV>(x, D, mean, rstd);
 #pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    const int e = hd * 64 + dsub * 4;
-    const float4 g0 = *reinterpret_cast<const float4*>(g3 + e), g1 = *reinterpret_cast<const float4*>(g3 + e + 32);
-    const float4 c0v = *reinterpret_cast<const float4*>(b3 + e), c1v = *reinterpret_cast<const float4*>(b3 + e + 32);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = (x[hd][i] - mean) * rstd * g[i] + bb[i];
-    if (live) {
-      const size_t off = row * D + e;
-      store_operand4(a_out, off, make_float4(y[0], y[1], y[2], y[3]));
-      store_operand4(a_out, off + 32, make_float4(y[4], y[5], y[6], y[7]));
-    }
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(g3 + e);
+    const float4 bb = *reinterpret_cast<const float4*>(b3 + e);
+    float4 o;
+    o.x = (x[4 * i + 0] - mean) * rstd * g.x + bb.x;
+    o.y = (x[4 * i + 1] - mean) * rstd * g.y + bb.y;
+    o.z = (x[4 * i + 2] - mean) * rstd * g.z + bb.z;
+    o.w = (x[4 * i + 3] - mean) * rstd * g.w + bb.w;
+    store_operand4(a_out, row * D + e, o);
   }
 }
 

@@ -417,7 +417,7 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
     const int r = i * 4 + rsub;
     float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
     x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-    if (MODE == EPI_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+    if (MODE == EPI_GELU) { x.x = gelu_erf_fast(x.x); x.y = gelu_erf_fast(x.y); x.z = gelu_erf_fast(x.z); x.w = gelu_erf_fast(x.w); }
     if (rot) {
       const float4 cs = aux.a[i];
       const float a0 = x.x, b0 = x.y, a1 = x.z, b1 = x.w;

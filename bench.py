@@ -287,7 +287,7 @@ def main():
             ach = g["flops"] / (g["ms"] / 1e3) / 1e12
             issued = 3 if args.precision == "fp32" else 1
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": "tap_gemm_tc_kernel",
+                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": "tap_gemm_tc2_kernel (CTA-pair tcgen05 tap-GEMM; class tap_gemm_tc)",
                     "launches_per_sample": g["launches"], "avg_launch_us": g["ms"] * 1e3 / g["launches"],
                     "flops_per_launch": g["flops"] / g["launches"], "share_of_profiled_ms": g["ms"] / tot_prof,
                     "issued_mma_per_product": issued, "issued_frac": ach * issued / pk["bf16_sustained"],
