@@ -149,7 +149,7 @@ struct ConvNet {
   double* stats = nullptr;
   int stat_slots = 0, stat_next = 0;
   size_t slot_doubles = 0;
-  size_t buf_elems = 0;
+  size_t buf_elems = 0, op_elems = 0;
   int maxB = 0;
   GraphCache graphs;
 
@@ -170,13 +170,15 @@ struct ConvNet {
     AFTER_REQUIRE(v.shape.size() == 3 && v.shape[0] == cout && v.shape[1] == cin && v.shape[2] == k, AFTER_ESHAPE,
                   "tensor '" + prefix + ".weight_v' has an unexpected shape");
     const std::vector<float> w = folded(prefix);
-    std::vector<float> m((size_t)cout * k * cin);
+    // 16/32-channel inputs (both ends of the codec) are zero-padded to the 64-channel K granule of the tcgen05 path
+    const int cp = (tc_mode() && cin < 64 && cin % 4 == 0 && cout % 32 == 0 && in_phases == 1) ? 64 : cin;
+    std::vector<float> m((size_t)cout * k * cp, 0.f);
     for (int o = 0; o < cout; ++o)
       for (int c = 0; c < cin; ++c)
-        for (int kk = 0; kk < k; ++kk) m[((size_t)o * k + kk) * cin + c] = w[((size_t)o * cin + c) * k + kk];
+        for (int kk = 0; kk < k; ++kk) m[((size_t)o * k + kk) * cp + c] = w[((size_t)o * cin + c) * k + kk];
     const HostTensor& b = get(prefix + ".bias");
     AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
-    build_gemm_weight(L.w, *arena, m, b.data.data(), cout, cin, taps, tc_mode());
+    build_gemm_weight(L.w, *arena, m, b.data.data(), cout, cp, taps, tc_mode());
     L.cin = cin; L.cout = cout; L.in_phases = in_phases; L.out_phases = 1;
   }
 
@@ -244,11 +246,14 @@ struct ConvNet {
     a.be = arena->upload(b.data);
   }
 
-  void alloc_workspace(size_t elems_per_stream, int max_batch, int slots) {
+  // elems_per_stream: largest activation (frames x channels); op_elems_per_stream: largest conv operand, which may be
+  // channel-padded to 64 (see make_conv)
+  void alloc_workspace(size_t elems_per_stream, size_t op_elems_per_stream, int max_batch, int slots) {
     maxB = max_batch;
     buf_elems = elems_per_stream * (size_t)max_batch;
+    op_elems = std::max(elems_per_stream, op_elems_per_stream) * (size_t)max_batch;
     for (auto& b : buf) b = arena->alloc<float>(buf_elems);
-    alloc_operand(op, *arena, buf_elems, tc_mode(), true);
+    alloc_operand(op, *arena, op_elems, tc_mode(), true);
     stat_slots = slots;
     slot_doubles = (size_t)max_batch * 8 * 2;
     stats = arena->alloc<double>(slot_doubles * slots);
@@ -268,7 +273,9 @@ struct ConvNet {
   // operand <- act(norm(x)) in the format the consuming conv wants
   void produce(const float* x, const NormAct& a, const double* xstats, const ConvLayer& consumer, int B, int T, int C,
                cudaStream_t st) {
-    AFTER_REQUIRE((size_t)B * T * C <= buf_elems, AFTER_EINVAL, "activation exceeds the codec workspace");
+    const int Cp = consumer.w.Cin;  // >= C: operand channels the consumer's K loop walks (zero-padded)
+    AFTER_REQUIRE(Cp >= C && (size_t)B * T * C <= buf_elems && (size_t)B * T * Cp <= op_elems, AFTER_EINVAL,
+                  "activation exceeds the codec workspace");
     ActParams p;
     p.norm = a.norm; p.act = a.act;
     p.stats = xstats; p.groups = a.groups; p.gamma = a.gamma; p.beta = a.beta;
@@ -277,13 +284,13 @@ struct ConvNet {
     OperandOut o;
     if (tc_mode() && consumer.w.tc_ok) { o.hi = op.hi; o.lo = nprod() > 1 ? op.lo : nullptr; }
     else o.f32 = op.f32;
-    const int fpb = std::max(1, 16384 / C);
+    const int fpb = std::max(1, 8192 / Cp);
     dim3 grid(ceil_div(T, fpb), B);
     const size_t smem = (size_t)5 * C * sizeof(float);
-    const double el = (double)B * T * C;
-    ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 + (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
-    if (C % 4 == 0) act_operand_kernel<4><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
-    else act_operand_kernel<1><<<grid, 256, smem, st>>>(x, o, p, T, C, fpb);
+    const double el = (double)B * T;
+    ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 * C + Cp * (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
+    if (C % 4 == 0 && Cp % 4 == 0) act_operand_kernel<4><<<grid, 256, smem, st>>>(x, o, p, T, C, Cp, fpb);
+    else act_operand_kernel<1><<<grid, 256, smem, st>>>(x, o, p, T, C, Cp, fpb);
     AFTER_CUDA_CHECK(cudaGetLastError());
     AFTER_COUNT_LAUNCH();
   }
@@ -423,17 +430,19 @@ struct Codec : ConvNet {
 
     // ---- workspace: the largest activation (frames x channels) of either net at the longest input
     AFTER_REQUIRE(c.ae_max_samples % ratio == 0, AFTER_EINVAL, "ae_max_samples must be a multiple of the codec ratio");
-    size_t T = (size_t)(c.ae_max_samples / M), mx = T * std::max(c.ae_in_channels, out_c);
+    size_t T = (size_t)(c.ae_max_samples / M), mx = T * std::max(c.ae_in_channels, out_c), mxp = T * 64;
     for (int i = 0; i <= n_stages; ++i) {
       mx = std::max(mx, T * (size_t)ech[i]);
+      mxp = std::max(mxp, T * (size_t)std::max(ech[i], 64));
       if (i < n_stages) T /= c.ae_factors[i];
     }
     mx = std::max(mx, T * (size_t)c.ae_z_channels);
     for (int i = 0; i <= n_stages; ++i) {
       mx = std::max(mx, T * (size_t)dch[i]);
+      mxp = std::max(mxp, T * (size_t)std::max(dch[i], 64));
       if (i < n_stages) T *= c.ae_factors[n_stages - 1 - i];
     }
-    alloc_workspace(mx, c.max_batch, 2 * (n_stages * nb + 4) + 8);
+    alloc_workspace(mx, mxp, c.max_batch, 2 * (n_stages * nb + 4) + 8);
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
     sd = nullptr;
   }
@@ -583,7 +592,7 @@ struct StructureEncoder : ConvNet {
     }
     make_block(blocks[n], "net." + std::to_string(n), couts[n - 1], c.se_kernel_size, c.se_causal != 0);
     maxT = c.seq_len;
-    alloc_workspace((size_t)maxT * mxc, c.max_batch, 1);
+    alloc_workspace((size_t)maxT * mxc, (size_t)maxT * std::max(mxc, 64), c.max_batch, 1);
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
     sd = nullptr;
   }

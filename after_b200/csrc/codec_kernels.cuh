@@ -33,17 +33,32 @@ struct OperandOut {
   __nv_bfloat16* lo = nullptr;
 };
 
-__device__ __forceinline__ float snake_beta(float y, float a, float ib) {
-  const float s = sinf(y * a);
-  return fmaf(s * s, ib, y);
+// sin^2 has period pi: reduce r = x - k*pi (Cody-Waite, two-term pi) into [-pi/2, pi/2] and evaluate the odd Taylor
+// polynomial through r^11 there (|error| < 6e-8): fp32-accurate for |x| up to ~1e5, ~14 instructions instead of the
+// ~30 of sinf's general path.  (core.py:217-218 evaluates sin(alpha*x)**2 on un-normalised activations.)
+__device__ __forceinline__ float sin_squared(float x) {
+  const float k = rintf(x * 0.31830988618379067154f);
+  float r = fmaf(k, -3.14159274101257324219f, x);   // pi rounded to fp32
+  r = fmaf(k, 8.74227765734758577309e-8f, r);       // pi - fp32(pi) = -8.742e-8  (so subtracting k*pi adds +k*8.742e-8)
+  const float r2 = r * r;
+  float p = fmaf(r2, -2.50521083854417187751e-8f, 2.75573192239858906526e-6f);
+  p = fmaf(p, r2, -1.98412698412698412698e-4f);
+  p = fmaf(p, r2, 8.33333333333333333333e-3f);
+  p = fmaf(p, r2, -1.66666666666666666667e-1f);
+  p = fmaf(p, r2, 1.0f);
+  const float s = r * p;
+  return s * s;
 }
+__device__ __forceinline__ float snake_beta(float y, float a, float ib) { return fmaf(sin_squared(y * a), ib, y); }
 __device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
 
 // x (B, T, C) fp32 -> operand (B, T, C): act(norm(x)).  grid = (ceil(T / frames_per_block), B), 256 threads.
 // C % 4 == 0 is required for the vector path (C4 = C / 4 float4 per frame); a scalar variant handles the rest.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int frames_per_block) {
+act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int Cp, int frames_per_block) {
+  // Cp >= C: output channels [C, Cp) are written as zeros (operands of the few 16/32-channel layers are padded to the
+  // 64-channel K granule of the tensor-core path)
   extern __shared__ float sm[];  // mu[C], rs[C], be[C], al[C], ib[C]
   float* s_mu = sm;
   float* s_rs = sm + C;
@@ -75,25 +90,31 @@ act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int
   __syncthreads();
   const int t0 = blockIdx.x * frames_per_block;
   const int nt = min(frames_per_block, T - t0);
-  const size_t base = ((size_t)b * T + t0) * C;
-  const int per_frame = C / VEC;
+  const int per_frame = Cp / VEC;
   const int total = nt * per_frame;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int c = (i % per_frame) * VEC;
-    const size_t off = base + (size_t)i * VEC;
+    const int f = i / per_frame;
+    const int c = (i - f * per_frame) * VEC;
+    const size_t off = ((size_t)b * T + t0 + f) * Cp + c;
     float v[VEC];
-    if (VEC == 4) {
-      const float4 xv = *reinterpret_cast<const float4*>(x + off);
-      v[0] = xv.x; v[1 % VEC] = xv.y; v[2 % VEC] = xv.z; v[3 % VEC] = xv.w;
-    } else {
-      v[0] = x[off];
-    }
+    if (c < C) {
+      const size_t in_off = ((size_t)b * T + t0 + f) * C + c;
+      if (VEC == 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + in_off);
+        v[0] = xv.x; v[1 % VEC] = xv.y; v[2 % VEC] = xv.z; v[3 % VEC] = xv.w;
+      } else {
+        v[0] = x[in_off];
+      }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float y = (v[j] - s_mu[c + j]) * s_rs[c + j] + s_be[c + j];
-      if (p.act == ACT_SNAKE) y = snake_beta(y, s_al[c + j], s_ib[c + j]);
-      else if (p.act == ACT_SILU) y = silu(y);
-      v[j] = y;
+      for (int j = 0; j < VEC; ++j) {
+        float y = (v[j] - s_mu[c + j]) * s_rs[c + j] + s_be[c + j];
+        if (p.act == ACT_SNAKE) y = snake_beta(y, s_al[c + j], s_ib[c + j]);
+        else if (p.act == ACT_SILU) y = silu(y);
+        v[j] = y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = 0.f;
     }
     if (VEC == 4) {
       if (out.f32) *reinterpret_cast<float4*>(out.f32 + off) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);

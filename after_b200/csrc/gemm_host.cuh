@@ -56,9 +56,9 @@ inline CUtensorMap make_tmap_act(const void* ptr, int C, int P, int T, int B) {
   return m;
 }
 
-inline int pick_bn(int N) {
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
+inline int pick_bn(int N, int n_per_phase = 0) {
+  for (int bn : {128, 64, 32})
+    if (N % bn == 0 && (n_per_phase == 0 || n_per_phase % bn == 0)) return bn;
   return 32;
 }
 
@@ -138,7 +138,7 @@ inline void build_gemm_weight(GemmWeight& gw, Arena& arena, const std::vector<fl
     std::vector<float> b(bias_host, bias_host + N);
     gw.bias = arena.upload(b);
   }
-  gw.bn = pick_bn(N);
+  gw.bn = pick_bn(N, taps.n_per_phase);
   gw.tc_ok = tc_mode && Cin % tc::BK == 0 && N % 32 == 0 && (taps.n_per_phase == 0 || taps.n_per_phase % gw.bn == 0);
   if (gw.tc_ok) {
     const size_t n = w.size();
