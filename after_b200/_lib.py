@@ -57,6 +57,17 @@ class AfterConfig(C.Structure):
         ("se_kernel_size", C.c_int32),
         ("se_causal", C.c_int32),
         ("se_use_tanh", C.c_int32),
+        ("te_in_size", C.c_int32),
+        ("te_n_blocks", C.c_int32),
+        ("te_channels", C.c_int32 * MAX_STAGES),
+        ("te_kernel_sizes", C.c_int32 * MAX_STAGES),
+        ("te_dilations", C.c_int32 * MAX_STAGES),
+        ("te_res2net_scale", C.c_int32),
+        ("te_se_channels", C.c_int32),
+        ("te_attention_channels", C.c_int32),
+        ("te_out_dim", C.c_int32),
+        ("te_global_context", C.c_int32),
+        ("te_use_tanh", C.c_int32),
     ]
 
 
@@ -83,6 +94,11 @@ PROTOTYPES = {
     "after_ae_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "after_ae_decode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_structure_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_timbre_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_generate": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float,
+                                 C.c_float, C.c_void_p]),
+    "after_generate_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
+                                      C.c_float, C.c_float, C.c_void_p]),
     "after_launch_count": (C.c_int64, [_H]),
     "after_device_bytes": (C.c_int64, [_H]),
     "after_ae_ratio": (C.c_int, [_H]),

@@ -7,6 +7,7 @@
 #include "codec.cuh"
 #include "context.cuh"
 #include "denoiser.cuh"
+#include "ecapa.cuh"
 
 namespace after {
 std::atomic<int64_t> g_launches{0};
@@ -25,12 +26,15 @@ struct after_ctx {
   Denoiser denoiser;
   Codec codec;
   StructureEncoder structure;
-  bool have_codec = false, have_structure = false;
+  TimbreEncoder timbre;
+  bool have_codec = false, have_structure = false, have_timbre = false;
   // pinned staging for the *_host entry points
   float* pin = nullptr;
   size_t pin_floats = 0;
   float* dev_io = nullptr;
   size_t dev_io_floats = 0;
+  float* chain = nullptr;  // z_s | z_t | time_cond | cond | x scratch of after_generate
+  size_t chain_floats = 0;
   std::string err;
 };
 
@@ -151,6 +155,7 @@ int after_destroy(after_handle h) {
     h->arena.release();
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dev_io) cudaFree(h->dev_io);
+    if (h->chain) cudaFree(h->chain);
   }
   delete h;
   return AFTER_OK;
@@ -208,6 +213,12 @@ int after_finalize_weights(after_handle h, int precision) {
       AFTER_REQUIRE(h->cfg.se_n_blocks > 0, AFTER_EINVAL, "structure-encoder tensors loaded but after_config.se_n_blocks == 0");
       h->structure.finalize(h->cfg, h->tensors[AFTER_MODULE_STRUCTURE_ENCODER], precision, &h->arena);
       h->have_structure = true;
+      any = true;
+    }
+    if (!h->tensors[AFTER_MODULE_TIMBRE_ENCODER].empty()) {
+      AFTER_REQUIRE(h->cfg.te_n_blocks > 0, AFTER_EINVAL, "timbre-encoder tensors loaded but after_config.te_n_blocks == 0");
+      h->timbre.finalize(h->cfg, h->tensors[AFTER_MODULE_TIMBRE_ENCODER], &h->arena);
+      h->have_timbre = true;
       any = true;
     }
     AFTER_REQUIRE(any, AFTER_EMISSING, "no tensors were loaded");
@@ -319,6 +330,90 @@ int after_structure_encode(after_handle h, const float* z, float* time_cond, int
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
     h->bridge.enter(user);
     h->structure.forward(z, time_cond, B, T, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_timbre_encode(after_handle h, const float* z, float* cond, int B, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_timbre, AFTER_ESTATE, "no timbre-encoder weights on this handle");
+    AFTER_REQUIRE(z && cond, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->timbre.forward(z, cond, B, T, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+static void generate_device(after_handle h, const float* a_s, const float* a_t, const float* x0, float* out, int B,
+                            int64_t samples, int nb_steps, float g_t, float g_s, cudaStream_t st) {
+  AFTER_REQUIRE(h->denoiser.D > 0 && h->have_codec && h->have_structure && h->have_timbre, AFTER_ESTATE,
+                "after_generate needs denoiser, autoencoder, structure-encoder and timbre-encoder weights");
+  const int ratio = h->codec.ratio;
+  AFTER_REQUIRE(samples > 0 && samples % ratio == 0, AFTER_EINVAL, "samples must be a positive multiple of the codec ratio");
+  const int T = (int)(samples / ratio);
+  const Denoiser& d = h->denoiser;
+  AFTER_REQUIRE(d.C == h->cfg.ae_z_channels && d.C == h->cfg.se_in_size && d.C == h->cfg.te_in_size, AFTER_EINVAL,
+                "latent channel counts of the sub-models disagree");
+  const size_t nz = (size_t)B * d.C * T, ntc = (size_t)B * d.zs * T, nc = (size_t)B * d.zt;
+  const size_t need = 3 * nz + ntc + nc;
+  if (need > h->chain_floats) {
+    if (h->chain) cudaFree(h->chain);
+    h->chain = nullptr;
+    AFTER_CUDA_CHECK(cudaMalloc(&h->chain, need * sizeof(float)));
+    h->chain_floats = need;
+  }
+  float* z_s = h->chain;
+  float* z_t = z_s + nz;
+  float* x = z_t + nz;
+  float* tcond = x + nz;
+  float* cond = tcond + ntc;
+  h->codec.encode(a_s, z_s, B, samples, st);
+  h->codec.encode(a_t, z_t, B, samples, st);
+  h->structure.forward(z_s, tcond, B, T, st);
+  h->timbre.forward(z_t, cond, B, T, st);
+  h->denoiser.sample(x0, cond, tcond, x, B, T, nb_steps, g_t, g_s, AFTER_CFG_AUDIO, 0.01f, st);
+  h->codec.decode(x, out, B, T, st);
+}
+
+int after_generate(after_handle h, const float* audio_structure, const float* audio_timbre, const float* x0, float* audio_out,
+                   int B, int64_t samples, int nb_steps, float guidance_timbre, float guidance_structure, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(audio_structure && audio_timbre && x0 && audio_out, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    generate_device(h, audio_structure, audio_timbre, x0, audio_out, B, samples, nb_steps, guidance_timbre, guidance_structure,
+                    h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_generate_host(after_handle h, const float* audio_structure, const float* audio_timbre, const float* x0,
+                        float* audio_out, int B, int64_t samples, int nb_steps, float guidance_timbre,
+                        float guidance_structure, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(audio_structure && audio_timbre && x0 && audio_out, AFTER_EINVAL, "null tensor pointer");
+    AFTER_REQUIRE(B >= 1 && samples >= 1 && h->have_codec, AFTER_EINVAL, "bad batch / samples, or no codec on this handle");
+    const int ratio = h->codec.ratio;
+    AFTER_REQUIRE(samples % ratio == 0, AFTER_EINVAL, "samples must be a multiple of the codec ratio");
+    const size_t na = (size_t)B * samples, nx = (size_t)B * h->denoiser.C * (samples / ratio);
+    ensure_staging(h, 3 * na + nx);
+    float* d_s = h->dev_io;
+    float* d_t = d_s + na;
+    float* d_o = d_t + na;
+    float* d_x = d_o + na;
+    cudaStream_t st = h->bridge.work;
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(d_s, audio_structure, na * 4, cudaMemcpyHostToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(d_t, audio_timbre, na * 4, cudaMemcpyHostToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(d_x, x0, nx * 4, cudaMemcpyHostToDevice, st));
+    generate_device(h, d_s, d_t, d_x, d_o, B, samples, nb_steps, guidance_timbre, guidance_structure, st);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(audio_out, d_o, na * 4, cudaMemcpyDeviceToHost, st));
+    AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
     h->bridge.exit(user);
   });
 }

@@ -53,6 +53,26 @@ class Encoder1D:
         return self
 
 
+class ECAPATDNN:
+    """Timbre encoder ``encoder(z)`` -- ecapa_encoder.py:567-624: (B, C, T) -> (B, zt)."""
+
+    def __init__(self, engine: Engine):
+        if not engine.has_timbre:
+            raise RuntimeError("engine was created without timbre-encoder weights")
+        self.engine = engine
+
+    def __call__(self, z):
+        return self.forward(z)
+
+    def forward(self, z):
+        return self.engine.timbre_encode(z)
+
+    forward_stream = forward  # identical arithmetic in the reference (ecapa_encoder.py:626-666)
+
+    def eval(self):
+        return self
+
+
 class RectifiedFlow:
     """``RectifiedFlow(net=, sr=, encoder=, encoder_time=, emb_model=, drop_value=)`` -- model.py:570, 721-785.
 

@@ -11,11 +11,11 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .config import AutoEncoderConfig, DenoiserConfig, Encoder1DConfig, ModelConfig
+from .config import AutoEncoderConfig, DenoiserConfig, EcapaConfig, Encoder1DConfig, ModelConfig
 
 
 def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], max_batch: int, max_steps: int,
-                 seq_len: Optional[int], max_samples: int, use_structure: bool) -> L.AfterConfig:
+                 seq_len: Optional[int], max_samples: int, use_structure: bool, use_timbre: bool = False) -> L.AfterConfig:
     c = L.AfterConfig()
     c.abi_version = L.ABI_VERSION
     d: DenoiserConfig = model.denoiser if model is not None else DenoiserConfig()
@@ -64,6 +64,23 @@ def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], 
         c.se_kernel_size = se.kernel_size
         c.se_causal = int(se.causal)
         c.se_use_tanh = int(se.use_tanh)
+    te: Optional[EcapaConfig] = model.timbre_encoder if (model is not None and use_timbre) else None
+    if te is not None:
+        n = len(te.channels)
+        if n > L.MAX_STAGES:
+            raise ValueError("too many timbre-encoder stages")
+        c.te_in_size = te.in_size
+        c.te_n_blocks = n
+        for i in range(n):
+            c.te_channels[i] = te.channels[i]
+            c.te_kernel_sizes[i] = te.kernel_sizes[i]
+            c.te_dilations[i] = te.dilations[i]
+        c.te_res2net_scale = te.res2net_scale
+        c.te_se_channels = te.se_channels
+        c.te_attention_channels = te.attention_channels
+        c.te_out_dim = te.out_dim
+        c.te_global_context = int(te.global_context)
+        c.te_use_tanh = int(te.use_tanh)
     return c
 
 
@@ -76,6 +93,7 @@ class Engine:
                  denoiser_state: Optional[Dict[str, torch.Tensor]] = None,
                  autoencoder_state: Optional[Dict[str, torch.Tensor]] = None,
                  structure_state: Optional[Dict[str, torch.Tensor]] = None,
+                 timbre_state: Optional[Dict[str, torch.Tensor]] = None,
                  precision: str = "fp32",
                  device: int = 0,
                  max_batch: int = 8,
@@ -91,7 +109,7 @@ class Engine:
         self.model_cfg = model
         self.ae_cfg = autoencoder
         self.cfg = _fill_config(model, autoencoder if autoencoder_state is not None else None, max_batch, max_steps,
-                                seq_len, max_samples, structure_state is not None)
+                                seq_len, max_samples, structure_state is not None, timbre_state is not None)
         L.check(self._lib.after_create(C.byref(self.cfg), device, C.byref(self._h)), None, "after_create")
         try:
             if denoiser_state is not None:
@@ -100,7 +118,9 @@ class Engine:
                 self._load(L.MODULE_AUTOENCODER, autoencoder_state)
             if structure_state is not None:
                 self._load(L.MODULE_STRUCTURE_ENCODER, structure_state)
-            if denoiser_state is not None or autoencoder_state is not None or structure_state is not None:
+            if timbre_state is not None:
+                self._load(L.MODULE_TIMBRE_ENCODER, timbre_state)
+            if any(s is not None for s in (denoiser_state, autoencoder_state, structure_state, timbre_state)):
                 L.check(self._lib.after_finalize_weights(self._h, L.PRECISIONS[precision]), self._h,
                         "after_finalize_weights")
         except Exception:
@@ -109,6 +129,7 @@ class Engine:
         self.has_denoiser = denoiser_state is not None
         self.has_codec = autoencoder_state is not None
         self.has_structure = structure_state is not None
+        self.has_timbre = timbre_state is not None
 
     # ------------------------------------------------------------------ plumbing
     def _load(self, module: int, sd: Dict[str, torch.Tensor]):
@@ -267,6 +288,42 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(self._lib.after_structure_encode(self._h, z.data_ptr(), out.data_ptr(), B, T, self._stream()), self._h,
                     "after_structure_encode")
+        return out
+
+    def timbre_encode(self, z):
+        z = self._dev(z, "z")
+        B, Cin, T = z.shape
+        if Cin != self.cfg.te_in_size:
+            raise ValueError(f"z must have {self.cfg.te_in_size} channels")
+        out = torch.empty(B, self.cfg.te_out_dim, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_timbre_encode(self._h, z.data_ptr(), out.data_ptr(), B, T, self._stream()), self._h,
+                    "after_timbre_encode")
+        return out
+
+    def generate(self, audio_structure, audio_timbre, x0, nb_steps, guidance_timbre=1.0, guidance_structure=1.0):
+        """Whole audio-to-audio chain on device tensors: (B,1,S) x2 + prior noise (B,C,S/ratio) -> audio (B,1,S)."""
+        a_s, a_t, x0 = self._dev(audio_structure, "audio_structure"), self._dev(audio_timbre, "audio_timbre"), self._dev(x0, "x0")
+        B, _, S = a_s.shape
+        if a_t.shape != a_s.shape or tuple(x0.shape) != (B, self.cfg.n_channels, S // max(self.ae_ratio, 1)):
+            raise ValueError("audio_structure / audio_timbre / x0 shapes disagree")
+        out = torch.empty_like(a_s)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_generate(self._h, a_s.data_ptr(), a_t.data_ptr(), x0.data_ptr(), out.data_ptr(), B, S,
+                                             int(nb_steps), float(guidance_timbre), float(guidance_structure), self._stream()),
+                    self._h, "after_generate")
+        return out
+
+    def generate_host(self, audio_structure, audio_timbre, x0, out, nb_steps, guidance_timbre=1.0, guidance_structure=1.0):
+        """Same with HOST tensors (pinned for speed); ``out`` (B,1,S) is filled and returned."""
+        for name, t in (("audio_structure", audio_structure), ("audio_timbre", audio_timbre), ("x0", x0), ("out", out)):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous fp32 CPU tensor")
+        B, _, S = audio_structure.shape
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_generate_host(self._h, audio_structure.data_ptr(), audio_timbre.data_ptr(), x0.data_ptr(),
+                                                  out.data_ptr(), B, S, int(nb_steps), float(guidance_timbre),
+                                                  float(guidance_structure), self._stream()), self._h, "after_generate_host")
         return out
 
     def profile(self, on: bool):

@@ -231,6 +231,46 @@ def encoder1d_state_dict(cfg: Encoder1DConfig, seed: int = 0) -> StateDict:
     return sd
 
 
+# ----------------------------------------------------------------------------- ECAPA-TDNN
+def _tdnn(sd, r, prefix, in_c, out_c, k):
+    """``TDNNBlock``: plain (not weight-normed) conv -> ReLU -> BatchNorm1d (ecapa_encoder.py:85-138)."""
+    bound = 1.0 / math.sqrt(in_c * k)
+    sd[prefix + ".conv.conv.weight"] = r.uniform((out_c, in_c, k), -bound, bound)
+    sd[prefix + ".conv.conv.bias"] = r.uniform((out_c, ), -bound, bound)
+    _batchnorm(sd, r, prefix + ".norm", out_c)
+
+
+def _plain_conv(sd, r, prefix, in_c, out_c, k=1):
+    bound = 1.0 / math.sqrt(in_c * k)
+    sd[prefix + ".weight"] = r.uniform((out_c, in_c, k), -bound, bound)
+    sd[prefix + ".bias"] = r.uniform((out_c, ), -bound, bound)
+
+
+def ecapa_state_dict(cfg: EcapaConfig, seed: int = 0) -> StateDict:
+    """``ECAPATDNN`` (ecapa_encoder.py:458-566) with pooling, global context, groups == 1."""
+    r = _Rng(seed)
+    sd: StateDict = {}
+    ch, ks = cfg.channels, cfg.kernel_sizes
+    _tdnn(sd, r, "blocks.0", cfg.in_size, ch[0], ks[0])
+    for i in range(1, len(ch) - 1):
+        p = f"blocks.{i}"
+        _tdnn(sd, r, p + ".tdnn1", ch[i - 1], ch[i], 1)
+        sub = ch[i] // cfg.res2net_scale
+        for j in range(cfg.res2net_scale - 1):
+            _tdnn(sd, r, f"{p}.res2net_block.blocks.{j}", sub, sub, ks[i])
+        _tdnn(sd, r, p + ".tdnn2", ch[i], ch[i], 1)
+        _plain_conv(sd, r, p + ".se_block.conv1.conv", ch[i], cfg.se_channels)
+        _plain_conv(sd, r, p + ".se_block.conv2.conv", cfg.se_channels, ch[i])
+        if ch[i - 1] != ch[i]:
+            _plain_conv(sd, r, p + ".shortcut.conv", ch[i - 1], ch[i])
+    _tdnn(sd, r, "mfa", ch[-1], ch[-1], ks[-1])
+    _tdnn(sd, r, "asp.tdnn", ch[-1] * (3 if cfg.global_context else 1), cfg.attention_channels, 1)
+    _plain_conv(sd, r, "asp.conv.conv", cfg.attention_channels, ch[-1])
+    _batchnorm(sd, r, "asp_bn", 2 * ch[-1])
+    _plain_conv(sd, r, "fc.conv", 2 * ch[-1], cfg.out_dim)
+    return sd
+
+
 # ----------------------------------------------------------------------------- inputs
 def synth_inputs(batch: int, cfg: DenoiserConfig, seed: int = 1234, frames: int = None):
     """x0 / cond / time_cond the way SURVEY.md section 8d prescribes (host-generated, so that

@@ -199,8 +199,10 @@ def main():
     chain = not args.no_chain
     ae_sd = synth.autoencoder_state_dict(acfg, 0) if chain else None
     se_sd = synth.encoder1d_state_dict(mc.structure_encoder, 0) if (chain and mc.structure_encoder is not None) else None
+    te_sd = synth.ecapa_state_dict(mc.timbre_encoder, 0) if chain else None
     eng = Engine(model=mc, autoencoder=acfg if chain else None, denoiser_state=den_sd, autoencoder_state=ae_sd,
-                 structure_state=se_sd, precision=args.precision, device=local, max_batch=B, max_steps=NS, max_samples=CHUNK)
+                 structure_state=se_sd, timbre_state=te_sd, precision=args.precision, device=local, max_batch=B, max_steps=NS,
+                 max_samples=CHUNK)
     x0, cond, tc = x0_h.to(dev), cond_h.to(dev), tc_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -256,21 +258,28 @@ def main():
     # ---- full chain: real-time factor -----------------------------------------------------------------------------
     rtf = None
     if chain:
-        audio_s = synth.synth_audio(B, CHUNK, seed=7 + rank).to(dev)   # structure source
-        audio_t = synth.synth_audio(B, CHUNK, seed=107 + rank).to(dev)  # timbre source
+        audio_s = synth.synth_audio(B, CHUNK, seed=7 + rank)    # structure source
+        audio_t = synth.synth_audio(B, CHUNK, seed=107 + rank)  # timbre source
+        if se_sd is not None:
+            a_s_h, a_t_h = audio_s.pin_memory(), audio_t.pin_memory()
+            audio_out_h = torch.empty_like(a_s_h).pin_memory()
+            a_s_d, a_t_d = a_s_h.to(dev), a_t_h.to(dev)
 
-        def chain_step():
-            z_s = eng.ae_encode(audio_s)
-            z_t = eng.ae_encode(audio_t)  # noqa: F841  (timbre branch: ECAPA is a SURVEY 8f 'next' row; cond is supplied)
-            tcond = eng.structure_encode(z_s) if se_sd is not None else tc
-            z = eng.sample(x0, cond, tcond, NS, 2.0, 1.0)
-            return eng.ae_decode(z)
+            def chain_step():  # device-resident inputs
+                return eng.generate(a_s_d, a_t_d, x0, NS, 2.0, 1.0)
 
-        chain_step()
-        chain_ms, _ = timed(chain_step, args.steps)
-        rtf = {"value": B * world * (CHUNK / SR) * args.steps / (chain_ms / 1e3), "unit": "x real time",
-               "ms_per_chunk_batch": chain_ms / args.steps,
-               "chain": "2x AutoEncoder.encode + Encoder1D + sample(50 steps, CFG) + AutoEncoder.decode; timbre vector supplied"}
+            def chain_host_step():  # host buffers: H2D of 2 x audio + noise, D2H of the audio, inside the call
+                eng.generate_host(a_s_h, a_t_h, x0_h, audio_out_h, NS, 2.0, 1.0)
+
+            chain_step()
+            chain_ms, _ = timed(chain_step, args.steps)
+            chain_host_step()
+            chain_host_ms, _ = timed(chain_host_step, args.steps)
+            audio_s_total = B * world * (CHUNK / SR) * args.steps
+            rtf = {"value": audio_s_total / (chain_ms / 1e3), "unit": "x real time", "ms_per_chunk_batch": chain_ms / args.steps,
+                   "e2e_value": audio_s_total / (chain_host_ms / 1e3), "e2e_ms_per_chunk_batch": chain_host_ms / args.steps,
+                   "e2e_h2d_bytes_per_step": int(4 * (2 * a_s_h.numel() + x0_h.numel())), "e2e_d2h_bytes_per_step": int(4 * audio_out_h.numel()),
+                   "chain": "after_generate: 2x AutoEncoder.encode + Encoder1D + ECAPATDNN + sample(50 steps, CFG) + AutoEncoder.decode"}
 
     # ---- roofline of the dominant kernel (tcgen05 tap-GEMM), per-launch CUDA events on the launching stream ----------
     pk = peaks()

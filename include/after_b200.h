@@ -105,6 +105,18 @@ typedef struct after_config {
   int32_t se_kernel_size;                  /* 5 */
   int32_t se_causal;                       /* 1: convs.get_padding.mode = 'causal' (base.gin:55) */
   int32_t se_use_tanh;
+  /* --- ECAPATDNN timbre encoder (ecapa_encoder.py:458-566); te_n_blocks == 0 disables --- */
+  int32_t te_in_size;
+  int32_t te_n_blocks;                       /* len(channels) (4) */
+  int32_t te_channels[AFTER_MAX_STAGES];     /* [512, 512, 512, 1024] */
+  int32_t te_kernel_sizes[AFTER_MAX_STAGES]; /* [3, 3, 3, 3] */
+  int32_t te_dilations[AFTER_MAX_STAGES];    /* [1, 1, 1, 1] */
+  int32_t te_res2net_scale;                  /* 8 */
+  int32_t te_se_channels;                    /* 128 */
+  int32_t te_attention_channels;             /* 128 */
+  int32_t te_out_dim;                        /* zt = 6 */
+  int32_t te_global_context;                 /* 1 */
+  int32_t te_use_tanh;
 } after_config;
 
 typedef struct after_ctx* after_handle;
@@ -163,6 +175,22 @@ int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, 
 
 /* Encoder1D.forward (encoder.py:273-298): z dev (B,C,T) -> time_cond dev (B,zs,T). */
 int after_structure_encode(after_handle h, const float* z, float* time_cond, int B, int T, void* stream);
+
+/* ECAPATDNN.forward (ecapa_encoder.py:567-624), the timbre encoder: z dev (B,C,T) -> cond dev (B,zt). */
+int after_timbre_encode(after_handle h, const float* z, float* cond, int B, int T, void* stream);
+
+/* The whole audio-to-audio chain of the notebooks (notebooks/audio_to_audio_demo.ipynb cells 5/19):
+ *   z_s = encode(audio_structure); z_t = encode(audio_timbre); time_cond = encoder_time(z_s); cond = encoder(z_t);
+ *   x = sample(x0, cond, time_cond, nb_steps, g_t, g_s); audio_out = decode(x)
+ * audio_* dev (B,1,S), x0 dev (B,C,S/ratio) (the prior noise is an INPUT so results are reproducible), out dev (B,1,S).
+ * Needs denoiser, autoencoder, structure- and timbre-encoder weights on the handle.  after_generate_host is the same
+ * with HOST buffers (H2D of the two audio batches and x0, D2H of the audio, stream synchronised before returning). */
+int after_generate(after_handle h, const float* audio_structure, const float* audio_timbre, const float* x0,
+                   float* audio_out, int B, int64_t samples, int nb_steps, float guidance_timbre,
+                   float guidance_structure, void* stream);
+int after_generate_host(after_handle h, const float* audio_structure, const float* audio_timbre, const float* x0,
+                        float* audio_out, int B, int64_t samples, int nb_steps, float guidance_timbre,
+                        float guidance_structure, void* stream);
 
 /* Introspection for benchmarks: kernels launched by this handle since creation, bytes of device
  * memory held, codec ratio (samples per latent frame). */

@@ -329,3 +329,66 @@ def encoder1d_forward(sd: StateDict, cfg, z: Tensor) -> Tensor:
         x = _wn_conv(sd, f"net.{i}.net.1", x)
     x = _v2_conv_block(sd, f"net.{n}", x, cfg.causal)
     return torch.tanh(x) if cfg.use_tanh else x
+
+
+# =============================================================================
+# Timbre encoder (after/diffusion/networks/ecapa_encoder.py)
+# =============================================================================
+def _reflect_conv(sd, prefix, x, dilation=1):
+    """``Conv1dSamePaddingReflect`` (stride 1): reflect-pad (k-1)*d/2 each side; ecapa_encoder.py:12-82."""
+    w = sd[prefix + ".weight"]
+    pad = (w.shape[-1] - 1) * dilation // 2
+    if pad:
+        x = F.pad(x, (pad, pad), mode="reflect")
+    return F.conv1d(x, w, sd[prefix + ".bias"], dilation=dilation)
+
+
+def _tdnn(sd, prefix, x, dilation=1):
+    """conv -> ReLU -> BatchNorm(eval); ecapa_encoder.py:85-138."""
+    return _bn_eval(sd, prefix + ".norm", torch.relu(_reflect_conv(sd, prefix + ".conv.conv", x, dilation)))
+
+
+def _attentive_stats(x, w, eps=1e-12):
+    mean = (w * x).sum(dim=2)
+    std = torch.sqrt((w * (x - mean.unsqueeze(2))**2).sum(dim=2).clamp(eps))
+    return mean, std
+
+
+def ecapa_forward(sd: StateDict, cfg, z: Tensor) -> Tensor:
+    """``ECAPATDNN.forward`` (pooling, global context, groups == 1); ecapa_encoder.py:567-624, 141-455.
+    z (B, in_size, T) -> (B, out_dim)."""
+    sd = _cast(sd, z.dtype)
+    ch = cfg.channels
+    x = _tdnn(sd, "blocks.0", z, cfg.dilations[0])
+    feats = []
+    for i in range(1, len(ch) - 1):
+        p = f"blocks.{i}"
+        res = _reflect_conv(sd, p + ".shortcut.conv", x) if (p + ".shortcut.conv.weight") in sd else x
+        y = _tdnn(sd, p + ".tdnn1", x)
+        parts = list(torch.chunk(y, cfg.res2net_scale, dim=1))  # Res2Net: chained sub-band TDNNs
+        outs = [parts[0]]
+        prev = None
+        for j in range(cfg.res2net_scale - 1):
+            inp = parts[j + 1] if j == 0 else parts[j + 1] + prev
+            prev = _tdnn(sd, f"{p}.res2net_block.blocks.{j}", inp, cfg.dilations[i])
+            outs.append(prev)
+        y = _tdnn(sd, p + ".tdnn2", torch.cat(outs, dim=1))
+        s = y.mean(dim=2, keepdim=True)  # squeeze-excitation
+        s = torch.relu(_reflect_conv(sd, p + ".se_block.conv1.conv", s))
+        s = torch.sigmoid(_reflect_conv(sd, p + ".se_block.conv2.conv", s))
+        x = s * y + res
+        feats.append(x)
+    x = _tdnn(sd, "mfa", torch.cat(feats, dim=1), cfg.dilations[-1])
+    # attentive statistics pooling
+    T = x.shape[-1]
+    if cfg.global_context:
+        mean, std = _attentive_stats(x, torch.tensor(1.0 / T, dtype=x.dtype))
+        a = torch.cat([x, mean.unsqueeze(2).expand(-1, -1, T), std.unsqueeze(2).expand(-1, -1, T)], dim=1)
+    else:
+        a = x
+    a = _reflect_conv(sd, "asp.conv.conv", torch.tanh(_tdnn(sd, "asp.tdnn", a)))
+    a = torch.softmax(a, dim=2)
+    mean, std = _attentive_stats(x, a)
+    v = _bn_eval(sd, "asp_bn", torch.cat([mean, std], dim=1).unsqueeze(2))
+    out = _reflect_conv(sd, "fc.conv", v).squeeze(2)
+    return torch.tanh(out) if cfg.use_tanh else out

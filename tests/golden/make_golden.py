@@ -125,6 +125,15 @@ def main():
         z = torch.randn(2, ecfg.in_size, 40, generator=g)
         save(f"encoder1d_{name}", weight_seed=wseed, z=z, out=enc(z))
 
+    # ---- timbre encoder (ECAPA-TDNN) ------------------------------------------------------------
+    for name, wseed in (("tiny", 51), ("base", 52)):
+        ecfg = config.get_config(name).timbre_encoder
+        enc = R.build_ecapa(name)
+        enc.load_state_dict(synth.ecapa_state_dict(ecfg, wseed), strict=True)
+        g = torch.Generator().manual_seed(400 + wseed)
+        z = torch.randn(2, ecfg.in_size, 40, generator=g)
+        save(f"ecapa_{name}", weight_seed=wseed, z=z, out=enc(z))
+
 
 if __name__ == "__main__":
     main()

@@ -98,6 +98,62 @@ def test_structure_encoder_matches_reference(golden, name, precision):
         eng.close()
 
 
+@pytest.mark.parametrize("name", ["tiny", "base"])
+def test_timbre_encoder_matches_reference(golden, name):
+    from after_b200.engine import Engine
+    from after_b200.diffusion import ECAPATDNN
+    from oracle import after_oracle as O
+    g = golden(f"ecapa_{name}")
+    mc = config.get_config(name)
+    sd = synth.ecapa_state_dict(mc.timbre_encoder, int(g["weight_seed"]))
+    z = T(g["z"])
+    eng = Engine(model=mc, timbre_state=sd, precision="fp32", max_batch=4, seq_len=256)
+    try:
+        enc = ECAPATDNN(eng)
+        out = enc(z.cuda())
+        assert out.shape == g["out"].shape
+        e = rel(out, g["out"])
+        print(f"ecapa_{name}: {e:.2e}")
+        assert e < 1e-4
+        # full-length chunk (T = 256), B = 3, oracle as checker
+        z2 = torch.randn(3, 64, 256, generator=torch.Generator().manual_seed(9))
+        assert rel(enc(z2.cuda()), O.ecapa_forward(sd, mc.timbre_encoder, z2)) < 1e-4
+    finally:
+        eng.close()
+
+
+def test_generate_chain_matches_oracle():
+    """after_generate / after_generate_host (2x encode -> Encoder1D + ECAPA -> sample -> decode) vs the oracle chain."""
+    from after_b200.engine import Engine
+    from oracle import after_oracle as O
+    mc = config.get_config("tiny")
+    acfg = config.base_autoencoder()
+    sds = dict(den=synth.denoiser_state_dict(mc.denoiser, 1), ae=synth.autoencoder_state_dict(acfg, 2),
+               se=synth.encoder1d_state_dict(mc.structure_encoder, 3), te=synth.ecapa_state_dict(mc.timbre_encoder, 4))
+    B, frames, steps = 2, 8, 3
+    S = frames * acfg.ratio
+    eng = Engine(model=mc, autoencoder=acfg, denoiser_state=sds["den"], autoencoder_state=sds["ae"], structure_state=sds["se"],
+                 timbre_state=sds["te"], precision="fp32", max_batch=B, max_steps=steps, seq_len=frames, max_samples=S)
+    try:
+        a_s, a_t = synth.synth_audio(B, S, seed=21), synth.synth_audio(B, S, seed=22)
+        x0 = torch.randn(B, 64, frames, generator=torch.Generator().manual_seed(23))
+        z_s, z_t = O.ae_encode(sds["ae"], acfg, a_s), O.ae_encode(sds["ae"], acfg, a_t)
+        tcond = O.encoder1d_forward(sds["se"], mc.structure_encoder, z_s)
+        cond = O.ecapa_forward(sds["te"], mc.timbre_encoder, z_t)
+        x = O.sample(sds["den"], mc.denoiser, x0, cond, tcond, steps, 2.0, 1.0)
+        want = O.ae_decode(sds["ae"], acfg, x)
+        got = eng.generate(a_s.cuda(), a_t.cuda(), x0.cuda(), steps, 2.0, 1.0)
+        assert got.shape == want.shape
+        e = rel(got, want)
+        print(f"generate chain: {e:.2e}")
+        assert e < 1e-3
+        host_out = torch.empty(B, 1, S)
+        eng.generate_host(a_s, a_t, x0, host_out, steps, 2.0, 1.0)
+        assert torch.equal(host_out, got.cpu())
+    finally:
+        eng.close()
+
+
 def test_codec_full_chunk_roundtrip_shape():
     """The reference's own self-check (export_autoencoder.py:50-54) at the north-star chunk: 524288 samples ->
     z (B, 64, 256) -> 524288 samples, finite."""

@@ -91,6 +91,16 @@ def test_encoder1d_matches_reference(golden, name):
     assert rel(out, g["out"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["tiny", "base"])
+def test_ecapa_matches_reference(golden, name):
+    g = golden(f"ecapa_{name}")
+    ecfg = config.get_config(name).timbre_encoder
+    sd = synth.ecapa_state_dict(ecfg, int(g["weight_seed"]))
+    out = O.ecapa_forward(sd, ecfg, T(g["z"]))
+    assert out.shape == g["out"].shape
+    assert rel(out, g["out"]) < 1e-5
+
+
 def test_codec_roundtrip_length():
     """The reference's own shape self-check (export_autoencoder.py:50-54): encode->decode keeps
     the length; 65536 samples -> z (1,64,32) -> 65536."""
