@@ -46,6 +46,8 @@ struct Denoiser {
   float *tcemb, *adaT, *E, *F1, *feat, *adaC;
   int *map_src, *map_trow, *map_tstride, *map_crow;
   float* guidance;
+  int* mlp_flags = nullptr;  // fused-MLP dependency counters: [L][row blocks]
+  int flag_stride = 0;
 
   // graph cache
   struct GraphEntry {
@@ -164,6 +166,8 @@ struct Denoiser {
     map_src = arena->alloc<int>(maxN); map_trow = arena->alloc<int>(maxN);
     map_tstride = arena->alloc<int>(maxN); map_crow = arena->alloc<int>(maxN);
     guidance = arena->alloc<float>(4);
+    flag_stride = maxN * ceil_div(maxT, 2 * tc::BM);
+    mlp_flags = arena->alloc<int>((size_t)L * flag_stride);
     const char* ng = getenv("AFTER_NO_GRAPH");
     use_graph = !(ng && ng[0] == '1');
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
@@ -263,6 +267,7 @@ struct Denoiser {
   // One network evaluation: x_src (n_src, C, T) channel-first -> proj [N*T, C] token-major.
   void run_network(const float* x_src, int n_src, int N, int T, const float* adaC_step, cudaStream_t st) {
     const int rows = N * T;
+    AFTER_CUDA_CHECK(cudaMemsetAsync(mlp_flags, 0, (size_t)L * flag_stride * sizeof(int), st));
     {
       dim3 grid(ceil_div(T, 4), n_src);
       patch_embed_kernel<4><<<grid, 256, C * 4 * sizeof(float), st>>>(x_src, pe_wt, pe_b, h0, C, T, D);
@@ -278,14 +283,16 @@ struct Denoiser {
       }
       attn(l, adaC_step, rows, T, st);
       {
-        GemmEpi e; e.ldo = HID; e.gelu = 1;
-        e.out_f32 = hid_op.f32; e.out_hi = hid_op.hi; e.out_lo = nprod() > 1 ? hid_op.lo : nullptr;
-        gemm(layers[l].mlp0, a_op, N, T, e, st);
-      }
-      {
-        GemmEpi e; e.out_f32 = h; e.ldo = D; e.res = h;
-        if (l == L - 1 && tc_mode()) { e.out_hi = a_op.hi; e.out_lo = nprod() > 1 ? a_op.lo : nullptr; }
-        gemm(layers[l].mlp2, hid_op, N, T, e, st);
+        GemmEpi e0; e0.ldo = HID; e0.gelu = 1;
+        e0.out_f32 = hid_op.f32; e0.out_hi = hid_op.hi; e0.out_lo = nprod() > 1 ? hid_op.lo : nullptr;
+        GemmEpi e1; e1.out_f32 = h; e1.ldo = D; e1.res = h;
+        if (l == L - 1 && tc_mode()) { e1.out_hi = a_op.hi; e1.out_lo = nprod() > 1 ? a_op.lo : nullptr; }
+        // one persistent launch for both MLP projections when the shapes allow it, else two launches
+        int* fl = mlp_flags + (size_t)l * flag_stride;
+        if (!(tc_mode() && launch_mlp_fused(a_op, layers[l].mlp0, e0, hid_op, layers[l].mlp2, e1, N, T, precision, fl, st))) {
+          gemm(layers[l].mlp0, a_op, N, T, e0, st);
+          gemm(layers[l].mlp2, hid_op, N, T, e1, st);
+        }
       }
     }
     {

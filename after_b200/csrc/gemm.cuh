@@ -348,8 +348,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // block in v[32] (the TMEM 32x32b layout); the block is transposed through a per-warp shared-memory tile so that
 // afterwards lane l owns COLUMN l and the warp walks the rows: every global access (residual, fp32 / bf16 outputs,
 // RoPE table) is then one contiguous 128-byte (64-byte for bf16) row segment.  Frames >= T are skipped (uniform).
-constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per warp; 16-byte chunks XOR-swizzled by (row & 7): conflict-free both ways
-constexpr int EPI_WARPS = 8;                  // warps 2..9: TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2
 
 // Epilogue flavours of the pair kernel, resolved at compile time so that each instantiation carries only its own code:
 //   EPI_PLAIN : (+bias) (+residual) -> fp32 (and/or bf16 hi/lo), optional GroupNorm statistics
@@ -357,22 +355,24 @@ constexpr int EPI_WARPS = 8;                  // warps 2..9: TMEM lane quarter =
 //   EPI_GELU  : +bias, exact GELU -> bf16 hi/lo (and/or fp32)                      (MLP up-projection)
 enum EpiMode { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_GELU = 2 };
 
-// Global operands of one block's epilogue (residual rows or RoPE cos/sin rows), requested before the TMEM load.
+// Global operands of one half-block's epilogue (residual rows or RoPE cos/sin rows), requested before the TMEM load.
+// Half-block = 32 frames x 16 columns; transposed ownership: lane -> 4 consecutive columns (lane & 3) * 4 of rows
+// (lane >> 2) + 8 i, i = 0..3.
 struct EpiAux {
-  float4 a[8];
+  float4 a[4];
 };
 template <int MODE>
 __device__ __forceinline__ void epi_prefetch(const GemmEpi& e, EpiAux& aux, int b, int t_base, int T, int col0, int lane) {
-  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  const int c4 = (lane & 3) * 4, rsub = lane >> 2;
   const int col = col0 + c4;
   const int nvalid = T - t_base;
   if (MODE == EPI_PLAIN) {
     if (e.res) {
       const float* p = e.res + ((size_t)b * T + t_base + rsub) * e.ldo + col;
-      const size_t step = (size_t)4 * e.ldo;
+      const size_t step = (size_t)8 * e.ldo;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        aux.a[i] = (i * 4 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 4; ++i) {
+        aux.a[i] = (i * 8 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
         p += step;
       }
     }
@@ -381,41 +381,55 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi& e, EpiAux& aux, int 
     if (rot) {
       const float2* p = e.rope_tab + (size_t)(t_base + rsub) * e.rot_half + ((col & 63) >> 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        aux.a[i] = (i * 4 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(1.f, 0.f, 1.f, 0.f);
-        p += 4 * e.rot_half;
+      for (int i = 0; i < 4; ++i) {
+        aux.a[i] = (i * 8 + rsub) < nvalid ? *reinterpret_cast<const float4*>(p) : make_float4(1.f, 0.f, 1.f, 0.f);
+        p += 8 * e.rot_half;
       }
     }
   }
 }
 
-// Row-coalesced epilogue of one 32 (frames) x 32 (columns) accumulator block.  On entry lane l holds row l of the
-// block in v[32] (the TMEM 32x32b layout); the block is transposed through a per-warp XOR-swizzled shared-memory
-// tile so that afterwards lane l owns 4 consecutive COLUMNS (l & 7) * 4 of rows (l >> 3) + 4 i: every global access
-// (residual, fp32 / bf16 outputs, RoPE table) is then a contiguous 128-byte (64-byte for bf16) row segment.
+// hi/lo bf16 split of four values with the packed converter: 2 cvt.rn.bf16x2 + 4 subtractions + 2 cvt
+__device__ __forceinline__ void split4_bf16(const float4& x, uint2& hi, uint2& lo) {
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
+
+// Row-coalesced epilogue of one 32 (frames) x 16 (columns) accumulator half-block.  On entry lane l holds row l in
+// v[16] (the TMEM 32x32b layout); the half-block is transposed through a per-warp 2 KB shared-memory tile (16-byte
+// chunks XOR-swizzled by (row >> 1) & 3: conflict-free both ways) so that afterwards every global access (residual,
+// fp32 / bf16 outputs, RoPE table) is a contiguous 64-byte (32-byte for bf16) row segment = whole 32-byte sectors.
+// Sixteen epilogue warps (4 per scheduler) rather than eight: the epilogue is latency-bound per warp
+// (TMEM load -> smem transpose -> arithmetic -> store is one dependent chain), so resident warps are what scales it.
+constexpr int EPI_STAGE_BYTES = 32 * 16 * 4;  // per warp
+constexpr int EPI_WARPS = 16;                 // warps 2..17: TMEM lane quarter = warp & 3, column quarter = (warp - 2) >> 2
+
 template <int MODE>
 __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const uint32_t* v, const EpiAux& aux, float4 bias4, int b,
                                           int t_base, int T, int col0, int lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(stg + lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   __syncwarp();
-  const int c4 = (lane & 7) * 4;
-  const int rsub = lane >> 3;
-  const int col = col0 + c4;
+  const int cq = lane & 3;
+  const int rsub = lane >> 2;
+  const int col = col0 + cq * 4;
   const int nvalid = T - t_base;
   const bool rot = MODE == EPI_ROPE && (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
   const bool has_res = MODE == EPI_PLAIN && e.res != nullptr;
   const size_t off0 = ((size_t)b * T + t_base + rsub) * e.ldo + col;
-  const size_t step = (size_t)4 * e.ldo;
+  const size_t step = (size_t)8 * e.ldo;
   float* pf = e.out_f32 ? e.out_f32 + off0 : nullptr;
   __nv_bfloat16* ph = e.out_hi ? e.out_hi + off0 : nullptr;
   __nv_bfloat16* pl = e.out_lo ? e.out_lo + off0 : nullptr;
   float ssum = 0.f, ssq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsub;
+    float4 x = *reinterpret_cast<const float4*>(stg + r * 16 + ((cq ^ ((r >> 1) & 3)) << 2));
     x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
     if (MODE == EPI_GELU) { x.x = gelu_erf_fast(x.x); x.y = gelu_erf_fast(x.y); x.z = gelu_erf_fast(x.z); x.w = gelu_erf_fast(x.w); }
     if (rot) {
@@ -432,10 +446,10 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
       }
       if (pf) *reinterpret_cast<float4*>(pf) = x;
       if (ph) {
-        __nv_bfloat16 hh[4], ll[4];
-        split_bf16(x.x, hh[0], ll[0]); split_bf16(x.y, hh[1], ll[1]); split_bf16(x.z, hh[2], ll[2]); split_bf16(x.w, hh[3], ll[3]);
-        *reinterpret_cast<uint2*>(ph) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
-        if (pl) *reinterpret_cast<uint2*>(pl) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+        uint2 hi, lo;
+        split4_bf16(x, hi, lo);
+        *reinterpret_cast<uint2*>(ph) = hi;
+        if (pl) *reinterpret_cast<uint2*>(pl) = lo;
       }
     }
     if (pf) pf += step;
@@ -443,12 +457,13 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
     if (pl) pl += step;
   }
   if (MODE == EPI_PLAIN && e.stats) {
-    // fold the 4 row sub-lanes (xor 8, 16) and the neighbouring 4-column lane (xor 1): lanes 0,2,4,6 then hold the
+    // fold the 8 row sub-lanes (xor 4, 8, 16) and the neighbouring 4-column lane (xor 1): lanes 0 and 2 then hold the
     // sums of 8 aligned columns, which always share a GroupNorm group here (channels per group % 8 == 0)
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);  ssq += __shfl_xor_sync(0xffffffffu, ssq, 4);
     ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);  ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
     ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
     ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);  ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
-    if ((lane & 0x19) == 0) {
+    if ((lane & 0x1D) == 0) {
       const int c = e.stat_cmod > 0 ? col % e.stat_cmod : col;
       double* p = e.stats + ((size_t)b * e.stat_groups + c / e.stat_cpg) * 2;
       atomicAdd(p, (double)ssum);
@@ -456,6 +471,14 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
     }
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
@@ -711,7 +734,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tmem_full = bars + 16;   // [2]
   uint64_t* tmem_empty = bars + 18;  // [2]  (leader's copies)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* epi_stage = reinterpret_cast<float*>(bars + 64);  // EPI_WARPS x [32][32], swizzled
+  float* epi_stage = reinterpret_cast<float*>(bars + 64);  // EPI_WARPS x [32][16], swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -834,20 +857,20 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       if (warp == 2 && lane == 0 && ti < 4) ts_mark(epi, 12 + 2 * ti);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-      float* stg = epi_stage + (warp - 2) * (32 * 32);
+      float* stg = epi_stage + (warp - 2) * (32 * 16);
       if (t_base < T) {
-        constexpr int HALF = BN / 2;  // this warp's column range: [chalf * HALF, +HALF)
-        const int cbeg = ((warp - 2) >> 2) * HALF;
+        constexpr int QCOLS = BN / 4;  // this warp's column range: [cq * QCOLS, +QCOLS)
+        const int cbeg = ((warp - 2) >> 2) * QCOLS;
 #pragma unroll 1
-        for (int c = cbeg; c < cbeg + HALF; c += 32) {
+        for (int c = cbeg; c < cbeg + QCOLS; c += 16) {
           EpiAux aux;
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (!(epi.debug_skip & 1)) {
             epi_prefetch<MODE>(epi, aux, b, t_base, T, n0 + c, lane);  // in flight during the TMEM load
-            if (epi.bias) bias4 = *reinterpret_cast<const float4*>(epi.bias + n0 + c + (lane & 7) * 4);
+            if (epi.bias) bias4 = *reinterpret_cast<const float4*>(epi.bias + n0 + c + (lane & 3) * 4);
           }
-          uint32_t v[32];
-          tmem_ld32_issue(taddr + c, v);
+          uint32_t v[16];
+          tmem_ld16_issue(taddr + c, v);
           tmem_ld_wait();
           epi_block<MODE>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
         }
@@ -866,6 +889,233 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   if (threadIdx.x == 32) ts_mark(epi, 21);
+}
+
+
+// =====================================================================================
+// Fused MLP: hidden = GELU(a W0^T + b0) and out = hidden W2^T + b2 + residual in ONE persistent launch of the pair
+// kernel.  Every cluster first works through its share of the up-projection tiles (problem 0), then through its
+// share of the down-projection tiles (problem 1); a down tile of row block mt may start once all up tiles of mt
+// have been stored, which the epilogues publish through a per-row-block counter in global memory
+// (threadfence + red.release  ->  ld.acquire + fence.proxy.async before the TMA reads the hidden activations).
+// What this buys over two launches: the down-projection mainloops overlap the un-hidden last epilogue of the
+// up-projection (write-bandwidth bound, ~5 us), one prologue/teardown/launch gap disappears, and the 48 down tiles
+// land on the clusters with the least up-projection work.  Deadlock-free because problem-0 tiles never wait and
+// precede problem-1 tiles in every cluster's list, and grid <= #SM pairs (all clusters co-resident).
+// =====================================================================================
+struct LinearProblem {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  GemmEpi epi;
+  int Cin;        // K
+  int n_tiles_n;  // N / BN
+  int n_tiles;    // n_tiles_n * (#row blocks)
+};
+
+__device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters, int n0, int n1, int& prob, int& tile) {
+  const int mine0 = cluster_id < n0 ? (n0 - cluster_id + n_clusters - 1) / n_clusters : 0;
+  if (i < mine0) {
+    prob = 0;
+    tile = cluster_id + i * n_clusters;
+    return true;
+  }
+  const int j = (n_clusters - 1 - cluster_id) + (i - mine0) * n_clusters;  // lightest clusters take problem 1 first
+  if (j < n1) {
+    prob = 1;
+    tile = j;
+    return true;
+  }
+  return false;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_constant__ LinearProblem p1, int T, int nprod,
+                     int m_tiles_per_b, int* __restrict__ flags, int flag_need, unsigned long long* dbg) {
+  auto mark = [&](int slot) {  // profiling experiments only: per-cluster %globaltimer marks of the leader CTA
+    if (dbg && (blockIdx.x & 1) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[(blockIdx.x >> 1) * 16 + slot] = t;
+    }
+  };
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int A_BYTES = Smem2<BN>::A_BYTES, B_BYTES = Smem2<BN>::B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  const int n_ops = nprod > 1 ? 2 : 1;
+  const int stage_bytes = n_ops * (A_BYTES + B_BYTES);
+  const int n_stages = nprod > 1 ? Smem2<BN>::stages(3) : Smem2<BN>::stages(1);
+
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)n_stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 8;
+  uint64_t* tmem_full = bars + 16;
+  uint64_t* tmem_empty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* epi_stage = reinterpret_cast<float*>(bars + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p0.a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p0.b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p1.a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p1.b_hi) : "memory");
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) mark(0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, prob, tile;
+      for (int i = 0; fused_item(i, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++i) {
+        const LinearProblem& p = prob ? p1 : p0;
+        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        const int b = mt / m_tiles_per_b;
+        const int t0 = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM;
+        const int nrow = nt * BN + (int)rank * (BN / 2);
+        if (prob == 1) {  // the hidden activations of row block mt must be complete and visible to the async proxy
+          mark(1);
+          int seen;
+          long long t_start = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + mt) : "memory");
+            if (seen < flag_need && clock64() - t_start > 4000000000LL) {
+              printf("after_b200: fused MLP dependency wait timeout (cluster %d, row block %d: %d of %d)\n", cluster_id, mt, seen, flag_need);
+              __trap();
+            }
+          } while (seen < flag_need);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mark(2);
+        }
+        const int cblocks = p.Cin / BK;
+        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t par = (it / n_stages) & 1;
+          mbar_wait(&empty[s], par ^ 1);
+          uint8_t* st = tiles + (size_t)s * stage_bytes;
+          const uint32_t fb = mapa(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
+          tma2_load_4d(&p.a_hi, fb, st, cb * BK, 0, t0, b);
+          tma2_load_2d(&p.b_hi, fb, st + A_BYTES, cb * BK, nrow);
+          if (nprod > 1) {
+            tma2_load_4d(&p.a_lo, fb, st + A_BYTES + B_BYTES, cb * BK, 0, t0, b);
+            tma2_load_2d(&p.b_lo, fb, st + 2 * A_BYTES + B_BYTES, cb * BK, nrow);
+          }
+        }
+        mark(prob ? 4 : 3);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc2(BN);
+      int it = 0, prob, tile;
+      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++ti) {
+        const int nkb = (prob ? p1.Cin : p0.Cin) / BK;
+        const int buf = ti & 1;
+        mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % n_stages;
+          const uint32_t par = (it / n_stages) & 1;
+          mbar_wait(&full[s], par);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
+          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + A_BYTES);
+          const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+          uint32_t accum = kb > 0;
+          if (nprod > 1) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) { umma2_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accum); accum = 1; }
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma2_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) { umma2_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accum); accum = 1; }
+          umma2_commit_mc(&empty[s]);
+        }
+        umma2_commit_mc(&tmem_full[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const uint32_t te0 = mapa(smem_u32(&tmem_empty[0]), 0), te1 = mapa(smem_u32(&tmem_empty[1]), 0);
+    int prob, tile;
+    for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++ti) {
+      const LinearProblem& p = prob ? p1 : p0;
+      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      const int b = mt / m_tiles_per_b;
+      const int t_base = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM + quad * 32;
+      const int n0 = nt * BN;
+      const int buf = ti & 1;
+      mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+      const bool tr = warp == 2 && lane == 0 && ti < 2;
+      if (tr) mark(8 + 4 * ti);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      float* stg = epi_stage + (warp - 2) * (32 * 16);
+      if (t_base < T) {
+        constexpr int QCOLS = BN / 4;
+        const int cbeg = ((warp - 2) >> 2) * QCOLS;
+#pragma unroll 1
+        for (int c = cbeg; c < cbeg + QCOLS; c += 16) {
+          EpiAux aux;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (prob == 0) {
+            if (p0.epi.bias) bias4 = *reinterpret_cast<const float4*>(p0.epi.bias + n0 + c + (lane & 3) * 4);
+          } else {
+            epi_prefetch<EPI_PLAIN>(p1.epi, aux, b, t_base, T, n0 + c, lane);
+            if (p1.epi.bias) bias4 = *reinterpret_cast<const float4*>(p1.epi.bias + n0 + c + (lane & 3) * 4);
+          }
+          uint32_t v[16];
+          tmem_ld16_issue(taddr + c, v);
+          tmem_ld_wait();
+          if (tr && c == cbeg) mark(9 + 4 * ti);
+          if (prob == 0) epi_block<EPI_GELU>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          else epi_block<EPI_PLAIN>(p1.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          if (tr && c == cbeg) mark(10 + 4 * ti);
+        }
+      }
+      if (tr) mark(11 + 4 * ti);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(buf ? te1 : te0);
+      if (prob == 0) {
+        // publish: every epilogue thread's stores -> gpu scope, then one release-increment per CTA
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        if (warp == 2 && lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + mt) : "memory");
+      }
+      if (warp == 2 && lane == 0) mark(prob ? 6 : 5);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) mark(7);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
 }
 
 }  // namespace tc

@@ -220,10 +220,86 @@ inline void tc_init_kernels() {
   set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_ROPE>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));  \
   set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_GELU>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));
   AFTER_SET_TC2(256)
+  set((const void*)tc::mlp_fused_tc2_kernel<256>, std::max(tc::Smem2<256>::total(3), tc::Smem2<256>::total(1)));
   AFTER_SET_TC2(128)
   AFTER_SET_TC2(64)
 #undef AFTER_SET_TC2
   done = true;
+}
+
+// Fused MLP launch (see mlp_fused_tc2_kernel).  Returns false when the shapes do not fit the fused kernel (the caller
+// then issues the two GEMMs separately).  `flags`: one zeroed int per 256-row block.
+inline bool use_fused_mlp() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AFTER_FUSED_MLP");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi0, ActOperand& hid, const GemmWeight& W2,
+                             GemmEpi epi1, int B, int T, int precision, int* flags, cudaStream_t st) {
+  constexpr int BN = 256;
+  if (precision == AFTER_PRECISION_FP32_SIMT || !use_pair_kernel() || !use_fused_mlp()) return false;
+  if (!W0.tc2_ok || !W2.tc2_ok || W0.bn2 != BN || W2.bn2 != BN || W0.taps.ntaps != 1 || W2.taps.ntaps != 1) return false;
+  if (W0.N != W2.Cin || epi0.out_hi != hid.hi || epi0.out_hi == nullptr || epi0.out_f32 != nullptr) return false;
+  static int n_pairs = 0;
+  if (!n_pairs) {
+    int dev = 0, sms = 0;
+    AFTER_CUDA_CHECK(cudaGetDevice(&dev));
+    AFTER_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    n_pairs = std::max(1, sms / 2);
+  }
+  const int nprod = precision == AFTER_PRECISION_BF16 ? 1 : 3;
+  const int m_tiles_per_b = ceil_div(T, 2 * tc::BM);
+  const int n_m_tiles = m_tiles_per_b * B;
+  epi0.bias = W0.bias;
+  epi1.bias = W2.bias;
+  tc::LinearProblem p0, p1;
+  const ActOperand::Maps& m0 = a_in.maps(W0.Cin, 1, T, B);
+  const ActOperand::Maps& m1 = hid.maps(W2.Cin, 1, T, B);
+  p0.a_hi = m0.hi; p0.a_lo = m0.lo; p0.b_hi = W0.map2_hi; p0.b_lo = W0.map2_lo; p0.epi = epi0; p0.Cin = W0.Cin;
+  p0.n_tiles_n = W0.N / BN; p0.n_tiles = p0.n_tiles_n * n_m_tiles;
+  p1.a_hi = m1.hi; p1.a_lo = m1.lo; p1.b_hi = W2.map2_hi; p1.b_lo = W2.map2_lo; p1.epi = epi1; p1.Cin = W2.Cin;
+  p1.n_tiles_n = W2.N / BN; p1.n_tiles = p1.n_tiles_n * n_m_tiles;
+  const int clusters = std::min(std::max(p0.n_tiles, p1.n_tiles), n_pairs);
+  const double rows = (double)B * T;
+  ProfScope prof(KC_TAP_GEMM_TC, st, 2.0 * rows * ((double)W0.N * W0.K + (double)W2.N * W2.K),
+                 rows * (W0.Cin * 4.0 + W0.N * 4.0 * 2 + W2.N * 8.0));
+  const int smem = tc::Smem2<BN>::total(nprod > 1 ? 3 : 1);
+  static int trace = -1;
+  static unsigned long long* dbg = nullptr;
+  if (trace < 0) {
+    const char* e = getenv("AFTER_DEBUG_TRACE_MLP");
+    trace = e ? atoi(e) : 0;  // trace the n-th fused launch (1-based), run with AFTER_NO_GRAPH=1
+    if (trace > 0) AFTER_CUDA_CHECK(cudaMalloc(&dbg, 128 * 16 * sizeof(unsigned long long)));
+  }
+  unsigned long long* dbg_now = nullptr;
+  if (trace > 0 && --trace == 0) {
+    dbg_now = dbg;
+    AFTER_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 128 * 16 * sizeof(unsigned long long), st));
+  }
+  tc::mlp_fused_tc2_kernel<BN><<<2 * clusters, tc::NUM_THREADS2, smem, st>>>(p0, p1, T, nprod, m_tiles_per_b, flags,
+                                                                             2 * p0.n_tiles_n, dbg_now);
+  AFTER_CUDA_CHECK(cudaGetLastError());
+  AFTER_COUNT_LAUNCH();
+  if (dbg_now) {
+    AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> hbuf(128 * 16);
+    AFTER_CUDA_CHECK(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < clusters; ++c) if (hbuf[c * 16]) t0 = std::min(t0, hbuf[c * 16]);
+    const char* names[16] = {"start", "p1_wait_begin", "p1_wait_end", "p0_loads_done", "p1_loads_done", "p0_epi_done", "p1_epi_done", "end",
+                             "e0_acc_ready", "e0_first_ld", "e0_first_blk", "e0_done", "e1_acc_ready", "e1_first_ld", "e1_first_blk", "e1_done"};
+    fprintf(stderr, "fused MLP trace (%d clusters; ns since first cluster start):\n", clusters);
+    for (int c = 0; c < clusters; c += (clusters > 16 ? clusters / 12 : 1)) {
+      fprintf(stderr, "  cluster %3d:", c);
+      for (int k = 0; k < 16; ++k) fprintf(stderr, " %s=%lld", names[k], hbuf[c * 16 + k] ? (long long)(hbuf[c * 16 + k] - t0) : -1LL);
+      fprintf(stderr, "\n");
+    }
+    trace = 0;
+  }
+  return true;
 }
 
 void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int groups, cudaStream_t st);
