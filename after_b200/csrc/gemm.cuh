@@ -431,7 +431,10 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
     const int r = i * 8 + rsub;
     float4 x = *reinterpret_cast<const float4*>(stg + r * 16 + ((cq ^ ((r >> 1) & 3)) << 2));
     x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-    if (MODE == EPI_GELU) { x.x = gelu_erf_fast(x.x); x.y = gelu_erf_fast(x.y); x.z = gelu_erf_fast(x.z); x.w = gelu_erf_fast(x.w); }
+    if (MODE == EPI_GELU) {
+      const float2 g0 = gelu_erf_fast2(make_float2(x.x, x.y)), g1 = gelu_erf_fast2(make_float2(x.z, x.w));
+      x = make_float4(g0.x, g0.y, g1.x, g1.y);
+    }
     if (rot) {
       const float4 cs = aux.a[i];
       const float a0 = x.x, b0 = x.y, a1 = x.z, b1 = x.w;

@@ -255,6 +255,10 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   const int n_m_tiles = m_tiles_per_b * B;
   epi0.bias = W0.bias;
   epi1.bias = W2.bias;
+  {
+    const char* e = getenv("AFTER_DEBUG_SKIP_EPILOGUE");
+    if (e) epi0.debug_skip = epi1.debug_skip = atoi(e);
+  }
   tc::LinearProblem p0, p1;
   const ActOperand::Maps& m0 = a_in.maps(W0.Cin, 1, T, B);
   const ActOperand::Maps& m1 = hid.maps(W2.Cin, 1, T, B);
