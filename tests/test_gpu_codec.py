@@ -167,3 +167,19 @@ def test_codec_full_chunk_roundtrip_shape():
         assert torch.isfinite(z).all() and torch.isfinite(y).all()
     finally:
         eng.close()
+
+
+def test_codec_single_frame():
+    """Shortest legal input: one latent frame (samples = ratio)."""
+    from oracle import after_oracle as O
+    acfg = config.base_autoencoder()
+    eng, sd, _ = codec_engine("base", 6, "fp32", 1, acfg.ratio)
+    try:
+        audio = synth.synth_audio(1, acfg.ratio, seed=13)
+        z_ref = O.ae_encode(sd, acfg, audio)
+        assert rel(eng.ae_encode(audio.cuda()), z_ref) < 1e-3
+        assert rel(eng.ae_decode(z_ref.cuda()), O.ae_decode(sd, acfg, z_ref)) < 1e-3
+        with pytest.raises(ValueError):
+            eng.ae_encode(audio[..., :-1].cuda())  # not a multiple of the codec ratio
+    finally:
+        eng.close()

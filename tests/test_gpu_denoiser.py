@@ -139,3 +139,55 @@ def test_errors_are_loud():
             eng.sample(x3.cuda(), c3.cuda(), t3.cuda(), 2)  # > max_batch
     finally:
         eng.close()
+
+
+def test_baseline_config_parity_50_steps():
+    """BASELINE configs[1] arithmetic at full length: base, T = 256, 50 Euler steps, CFG 2.0/1.0, fp32 mode vs the CPU
+    oracle (2 of the 8 streams: rows are independent, see test_full_size_properties) -- tolerance 1e-3 (north_star);
+    the bf16 mode's drift over the same 50 steps is reported and loosely gated."""
+    from oracle import after_oracle as O
+    eng, sd, mc = make_engine("base", 0, "fp32", 256, max_batch=2, max_steps=50)
+    try:
+        x0, cond, tc = synth.synth_inputs(2, mc.denoiser, seed=1234)
+        want = O.sample(sd, mc.denoiser, x0, cond, tc, 50, 2.0, 1.0)
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 50, 2.0, 1.0)
+        e = rel(got, want)
+        print(f"base T=256 50 steps fp32 mode: rel-L2 {e:.2e}")
+        assert e < 1e-3
+    finally:
+        eng.close()
+    eng, sd, mc = make_engine("base", 0, "bf16", 256, max_batch=2, max_steps=50)
+    try:
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 50, 2.0, 1.0)
+        e = rel(got, want)
+        print(f"base T=256 50 steps bf16 mode: rel-L2 {e:.2e}")
+        assert e < 1e-1
+    finally:
+        eng.close()
+
+
+def test_midi_config_full_length():
+    """BASELINE configs[3] arithmetic: midi (zs = 128 piano roll, window 16), MIDI CFG layout, T = 256."""
+    from oracle import after_oracle as O
+    eng, sd, mc = make_engine("midi", 5, "fp32", 256, max_batch=2, max_steps=6)
+    try:
+        x0, cond, tc = synth.synth_inputs(2, mc.denoiser, seed=77)
+        want = O.sample(sd, mc.denoiser, x0, cond, tc, 6, 2.0, 3.0, cfg_variant=1, clamp=0.1)
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 6, 2.0, 3.0, cfg_variant=1, clamp=0.1)
+        assert rel(got, want) < 1e-3
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("frames", [1, 2, 5])
+def test_degenerate_lengths(frames):
+    """Shortest sequences (a single frame, a ragged single chunk): every kernel's tail handling."""
+    from oracle import after_oracle as O
+    eng, sd, mc = make_engine("tiny", 9, "fp32", frames, max_batch=1, max_steps=2)
+    try:
+        x0, cond, tc = synth.synth_inputs(1, mc.denoiser, seed=3, frames=frames)
+        want = O.sample(sd, mc.denoiser, x0, cond, tc, 2, 1.0, 1.0)
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 2, 1.0, 1.0)
+        assert rel(got, want) < 2e-4
+    finally:
+        eng.close()
