@@ -334,7 +334,8 @@ patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ Wt, co
     const float bv = bias[d];
 #pragma unroll
     for (int tt = 0; tt < TPB_FRAMES; ++tt) acc[tt] = bv;
-    for (int c = 0; c < C; ++c) {
+#pragma unroll 16
+    for (int c = 0; c < C; ++c) {  // independent loads: unrolled so 16 weight fetches are in flight per thread
       const float w = Wt[(size_t)c * D + d];
 #pragma unroll
       for (int tt = 0; tt < TPB_FRAMES; ++tt) acc[tt] = fmaf(xs[c * TPB_FRAMES + tt], w, acc[tt]);
