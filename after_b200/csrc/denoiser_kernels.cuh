@@ -146,8 +146,10 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
     float4 q1 = *reinterpret_cast<const float4*>(qrow + 32);
     const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
     const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
-    q0.x *= 0.125f; q0.y *= 0.125f; q0.z *= 0.125f; q0.w *= 0.125f;  // 1/sqrt(64): exact power of two
-    q1.x *= 0.125f; q1.y *= 0.125f; q1.z *= 0.125f; q1.w *= 0.125f;
+    // scores are kept in the log2 domain: q is scaled by log2(e) / sqrt(64) once, so softmax needs only ex2
+    const float qs = 0.125f * 1.4426950408889634f;
+    const float2 qa = make_float2(q0.x * qs, q0.y * qs), qb = make_float2(q0.z * qs, q0.w * qs);
+    const float2 qc = make_float2(q1.x * qs, q1.y * qs), qd = make_float2(q1.z * qs, q1.w * qs);
     float s[MAXK];
 #pragma unroll
     for (int j = 0; j < MAXK; ++j) {
@@ -155,7 +157,11 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
       if (j < nk) {
         const float4 k0 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D));
         const float4 k1 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D) + 32);
-        s[j] = (q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w) + (q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w);
+        float2 acc = __fmul2_rn(qa, make_float2(k0.x, k0.y));  // packed fp32x2 FMAs: two lanes of the dot product each
+        acc = __ffma2_rn(qb, make_float2(k0.z, k0.w), acc);
+        acc = __ffma2_rn(qc, make_float2(k1.x, k1.y), acc);
+        acc = __ffma2_rn(qd, make_float2(k1.z, k1.w), acc);
+        s[j] = acc.x + acc.y;
       }
     }
     float m = -INFINITY;
@@ -170,18 +176,23 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
       m = fmaxf(m, v);
     }
     float l = 0.f;
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float2 o01 = make_float2(0.f, 0.f), o23 = o01, o45 = o01, o67 = o01;
 #pragma unroll
     for (int j = 0; j < MAXK; ++j) {
       if (j < nk) {
-        const float p = expf(s[j] - m);  // exp(-inf) = 0 for masked keys
+        float p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s[j] - m));  // 2^(-inf) = 0 for masked keys
         l += p;
         const float4 v0 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D));
         const float4 v1 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D) + 32);
-        o[0] = fmaf(p, v0.x, o[0]); o[1] = fmaf(p, v0.y, o[1]); o[2] = fmaf(p, v0.z, o[2]); o[3] = fmaf(p, v0.w, o[3]);
-        o[4] = fmaf(p, v1.x, o[4]); o[5] = fmaf(p, v1.y, o[5]); o[6] = fmaf(p, v1.z, o[6]); o[7] = fmaf(p, v1.w, o[7]);
+        const float2 pp = make_float2(p, p);
+        o01 = __ffma2_rn(pp, make_float2(v0.x, v0.y), o01);
+        o23 = __ffma2_rn(pp, make_float2(v0.z, v0.w), o23);
+        o45 = __ffma2_rn(pp, make_float2(v1.x, v1.y), o45);
+        o67 = __ffma2_rn(pp, make_float2(v1.z, v1.w), o67);
       }
     }
+    const float o[8] = {o01.x, o01.y, o23.x, o23.y, o45.x, o45.y, o67.x, o67.y};
     const float inv = 1.0f / l;
     float* xp = &xs[qi][hd * 64 + dsub * 4];
     *reinterpret_cast<float4*>(xp) = make_float4(fmaf(o[0], inv, r0.x), fmaf(o[1], inv, r0.y), fmaf(o[2], inv, r0.z), fmaf(o[3], inv, r0.w));
