@@ -1,0 +1,149 @@
+"""``Streamer``: the nn_tilde-facing method / attribute surface of ``after_scripts/export.py:145-507``, on top of an
+``Engine``.  Same method names, channel counts, ratios and attribute setters, so host code written against the exported
+model (notebooks/audio_to_audio_demo.ipynb cell 9, ``nn~ <model> generate_timbre 8192``) runs against it.
+
+Semantics: *block-offline*.  Every call processes its buffer with the offline (cache-free) kernels, i.e. what the
+reference computes with ``cc.use_cached_conv(False)`` and ``max_cache_size = 0``; the cross-buffer state the reference
+keeps in cached convolutions / per-step KV caches is not carried over.  The one piece
+of cross-call state that IS part of the method contract -- the rolling ``previous_timbre`` latent buffer -- is kept.
+TorchScript serialisation (``export_to_ts``) and the latent-map MLP (``latent2map`` / ``map2latent``) are out of scope.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .engine import Engine
+
+
+class Streamer:
+
+    def __init__(self, engine: Engine, n_signal_timbre: int = 64, chunk_size: int = 4, latent_range: float = 1.0):
+        if not (engine.has_denoiser and engine.has_codec and engine.has_structure and engine.has_timbre):
+            raise RuntimeError("Streamer needs denoiser, autoencoder, structure-encoder and timbre-encoder weights")
+        self.engine = engine
+        self.chunk_size = chunk_size
+        self.n_signal_timbre = n_signal_timbre
+        self.latent_range = latent_range
+        self.zs_channels = engine.cfg.tcond_dim
+        self.zt_channels = engine.cfg.cond_dim
+        self.ae_latents = engine.cfg.n_channels
+        self.ae_ratio = engine.ae_ratio
+        self.drop_value = engine.cfg.drop_value
+        self.sr = 44100
+        self.zt_buffer = n_signal_timbre * self.ae_ratio
+        # attributes are 1-tuples with get_/set_ accessors (export.py:180-182, 330-355)
+        self.nb_steps = (1, )
+        self.guidance_timbre = (1.0, )
+        self.guidance_structure = (1.0, )
+        # rolling latent history fed to the timbre encoder (export.py:185-187, 418-429)
+        self.previous_timbre = torch.zeros(4, self.ae_latents, n_signal_timbre, device=engine.device)
+        # (in_channels, in_ratio, out_channels, out_ratio) per method (export.py:190-328)
+        r = self.ae_ratio
+        self.methods = {
+            "forward": (2, 1, 1, 1),
+            "structure": (1, 1, self.zs_channels, r),
+            "timbre": (1, 1, self.zt_channels, r),
+            "diffuse": (self.zs_channels + self.zt_channels, r, self.ae_latents, r),
+            "generate": (self.zs_channels + self.zt_channels, r, 1, 1),
+            "generate_timbre": (self.zt_channels + 1, 1, 1, 1),
+            "decode": (self.ae_latents, r, 1, 1),
+        }
+
+    # ---- attributes ---------------------------------------------------------------------------
+    def get_guidance_timbre(self) -> float:
+        return self.guidance_timbre[0]
+
+    def set_guidance_timbre(self, guidance_timbre: float) -> int:
+        self.guidance_timbre = (float(guidance_timbre), )
+        return 0
+
+    def get_guidance_structure(self) -> float:
+        return self.guidance_structure[0]
+
+    def set_guidance_structure(self, guidance_structure: float) -> int:
+        self.guidance_structure = (float(guidance_structure), )
+        return 0
+
+    def get_nb_steps(self) -> int:
+        return self.nb_steps[0]
+
+    def set_nb_steps(self, nb_steps: int) -> int:
+        self.nb_steps = (int(nb_steps), )
+        return 0
+
+    # ---- methods --------------------------------------------------------------------------------
+    def _check(self, name: str, x: torch.Tensor):
+        cin = self.methods[name][0]
+        if x.dim() != 3 or x.shape[1] != cin:
+            raise ValueError(f"{name} expects (n_batch, {cin}, buffer), got {tuple(x.shape)}")
+        return x.to(self.engine.device, torch.float32).contiguous()
+
+    def sample(self, x_last, cond, time_cond):
+        """export.py:398-416 without the per-step KV caches; the streamer clamps the guidance ratio at 0.1 (:389-390)."""
+        return self.engine.sample(x_last, cond, time_cond, self.nb_steps[0], self.guidance_timbre[0],
+                                  self.guidance_structure[0], cfg_variant=L.CFG_AUDIO, clamp=0.1)
+
+    def timbre(self, x):
+        x = self._check("timbre", x)
+        z = self.engine.ae_encode(x)
+        n, t = z.shape[0], z.shape[-1]
+        hist = torch.cat((self.previous_timbre[:n], z), -1)[..., t:]
+        self.previous_timbre[:n] = hist
+        zsem = self.engine.timbre_encode(self.previous_timbre[:n].contiguous()) / self.latent_range
+        return zsem.unsqueeze(-1).repeat(1, 1, self.chunk_size)
+
+    def structure(self, x):
+        x = self._check("structure", x)
+        return self.engine.structure_encode(self.engine.ae_encode(x))
+
+    def diffuse(self, x, noise: Optional[torch.Tensor] = None):
+        """(n, zs + zt, T) -> (n, latents, T).  As in the reference only batch row 0 is sampled and the result is
+        repeated (export.py:437-449).  ``noise``: optional prior (n, latents, T); by default it is drawn from the global
+        torch RNG on the host, like the reference's ``torch.randn``."""
+        x = self._check("diffuse", x)
+        n, T = x.shape[0], x.shape[-1]
+        zsem = x[:, -self.zt_channels:].mean(-1) * self.latent_range
+        time_cond = x[:, :self.zs_channels]
+        if noise is None:
+            noise = torch.randn(n, self.ae_latents, T)
+        noise = noise.to(self.engine.device, torch.float32)
+        out = self.sample(noise[:1].contiguous(), zsem[:1].contiguous(), time_cond[:1].contiguous())
+        return out.repeat(n, 1, 1) if n > 1 else out
+
+    def diffuse_timbre(self, x, noise: Optional[torch.Tensor] = None):
+        x = self._check("generate_timbre", x)
+        n = x.shape[0]
+        zsem = x[:, 1:].mean(-1) * self.latent_range
+        time_cond = self.structure(x[:, :1].contiguous())
+        if noise is None:
+            noise = torch.randn(n, self.ae_latents, time_cond.shape[-1])
+        noise = noise.to(self.engine.device, torch.float32)
+        out = self.sample(noise[:1].contiguous(), zsem[:1].contiguous(), time_cond[:1].contiguous())
+        return out.repeat(n, 1, 1) if n > 1 else out
+
+    def decode(self, x):
+        return self.engine.ae_decode(self._check("decode", x))
+
+    def generate(self, x, noise: Optional[torch.Tensor] = None):
+        return self.decode(self.diffuse(x, noise))
+
+    def generate_timbre(self, x, noise: Optional[torch.Tensor] = None):
+        return self.decode(self.diffuse_timbre(x, noise))
+
+    def forward(self, x, noise: Optional[torch.Tensor] = None):
+        x = self._check("forward", x)
+        structure = self.structure(x[:, :1].contiguous())
+        timbre = self.timbre(x[:, 1:].contiguous())
+        if timbre.shape[-1] != structure.shape[-1]:  # chunk_size frames vs buffer / ratio frames
+            timbre = timbre[..., :1].repeat(1, 1, structure.shape[-1])
+        return self.decode(self.diffuse(torch.cat((structure, timbre), 1), noise))
+
+    __call__ = forward
+
+    def latent2map(self, x):
+        raise NotImplementedError("latent-map MLP (after/diffusion/latent_plot.py) is an export-time UI artefact: out of scope")
+
+    map2latent = latent2map

@@ -183,3 +183,44 @@ def test_codec_single_frame():
             eng.ae_encode(audio[..., :-1].cuda())  # not a multiple of the codec ratio
     finally:
         eng.close()
+
+
+def test_streamer_surface_matches_oracle_chain():
+    """nn_tilde-shaped ``Streamer`` (export.py:145-507): method shapes, attribute setters, rolling timbre buffer and
+    ``forward`` = structure | timbre -> diffuse -> decode, checked against the oracle with the same injected noise."""
+    from after_b200.engine import Engine
+    from after_b200.streamer import Streamer
+    from oracle import after_oracle as O
+    mc = config.get_config("tiny")
+    acfg = config.base_autoencoder()
+    sds = dict(den=synth.denoiser_state_dict(mc.denoiser, 1), ae=synth.autoencoder_state_dict(acfg, 2),
+               se=synth.encoder1d_state_dict(mc.structure_encoder, 3), te=synth.ecapa_state_dict(mc.timbre_encoder, 4))
+    n_sig = 16
+    eng = Engine(model=mc, autoencoder=acfg, denoiser_state=sds["den"], autoencoder_state=sds["ae"], structure_state=sds["se"],
+                 timbre_state=sds["te"], precision="fp32", max_batch=4, max_steps=8, seq_len=n_sig, max_samples=n_sig * acfg.ratio)
+    try:
+        st = Streamer(eng, n_signal_timbre=n_sig, chunk_size=4)
+        assert st.set_nb_steps(3) == 0 and st.get_nb_steps() == 3
+        st.set_guidance_timbre(2.0); st.set_guidance_structure(1.0)
+        assert st.get_guidance_timbre() == 2.0 and st.methods["diffuse"] == (12 + 6, acfg.ratio, 64, acfg.ratio)
+        frames = 4
+        audio = torch.cat([synth.synth_audio(2, frames * acfg.ratio, seed=31), synth.synth_audio(2, frames * acfg.ratio, seed=32)], 1)
+        noise = torch.randn(2, 64, frames, generator=torch.Generator().manual_seed(33))
+        got = st.forward(audio.cuda(), noise=noise)
+        assert got.shape == (2, 1, frames * acfg.ratio)
+        # oracle chain: timbre history = zeros rolled by the new latents; only row 0 is diffused, then repeated
+        z_s = O.ae_encode(sds["ae"], acfg, audio[:, :1])
+        z_t = O.ae_encode(sds["ae"], acfg, audio[:, 1:])
+        hist = torch.cat([torch.zeros(2, 64, n_sig), z_t], -1)[..., frames:]
+        cond = O.ecapa_forward(sds["te"], mc.timbre_encoder, hist)
+        tcond = O.encoder1d_forward(sds["se"], mc.structure_encoder, z_s)
+        x = O.sample(sds["den"], mc.denoiser, noise[:1], cond[:1], tcond[:1], 3, 2.0, 1.0, clamp=0.1)
+        want = O.ae_decode(sds["ae"], acfg, x).repeat(2, 1, 1)
+        e = rel(got, want)
+        print(f"streamer.forward: {e:.2e}")
+        assert e < 1e-3
+        assert torch.equal(st.previous_timbre[:2].cpu()[..., -frames:], eng.ae_encode(audio[:, 1:].cuda()).cpu())
+        with pytest.raises(ValueError):
+            st.decode(torch.zeros(1, 3, 4))
+    finally:
+        eng.close()
