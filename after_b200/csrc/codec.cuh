@@ -358,6 +358,7 @@ struct Codec : ConvNet {
   // filter banks
   float *pq_fwd = nullptr, *pq_inv = nullptr;
   int pq_fwd_k = 0, pq_inv_k = 0;
+  float *io_audio = nullptr, *io_z = nullptr;  // graph-stable staging of the public tensors
 
   void finalize(const after_config& c, const TensorMap& tensors, int prec, Arena* ar) {
     cfg = c; precision = prec; arena = ar; sd = &tensors;
@@ -443,6 +444,8 @@ struct Codec : ConvNet {
       if (i < n_stages) T *= c.ae_factors[n_stages - 1 - i];
     }
     alloc_workspace(mx, mxp, c.max_batch, 2 * (n_stages * nb + 4) + 8);
+    io_audio = arena->alloc<float>((size_t)c.max_batch * c.ae_max_samples);
+    io_z = arena->alloc<float>((size_t)c.max_batch * c.ae_z_channels * (c.ae_max_samples / ratio));
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
     sd = nullptr;
   }
@@ -496,12 +499,14 @@ struct Codec : ConvNet {
     AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
   }
 
+  // The captured graphs work on library-owned staging buffers (io_audio / io_z), so they never bake caller pointers
+  // in: one graph per (direction, B, length), replayed for any caller tensors.
   void encode(const float* audio, float* z, int B, int64_t samples, cudaStream_t st) {
     check(B, samples);
-    // graph nodes bake the I/O pointers in: key on them too
-    graphs.run({0, B, (int)(samples & 0x7fffffff), (int)((uintptr_t)audio & 0x7fffffff), (int)((uintptr_t)audio >> 31),
-                (int)((uintptr_t)z & 0x7fffffff), (int)((uintptr_t)z >> 31)},
-               st, [&] { encode_body(audio, z, B, samples, st); });
+    const int T = (int)(samples / ratio);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_audio, audio, (size_t)B * samples * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    graphs.run({0, B, (int)(samples & 0x7fffffff)}, st, [&] { encode_body(io_audio, io_z, B, samples, st); });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(z, io_z, (size_t)B * cfg.ae_z_channels * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
 
   // ------------------------------------------------------------------ AutoEncoder.decode
@@ -552,9 +557,9 @@ struct Codec : ConvNet {
   void decode(const float* z, float* audio, int B, int T, cudaStream_t st) {
     AFTER_REQUIRE(T >= 1, AFTER_EINVAL, "T must be >= 1");
     check(B, (int64_t)T * ratio);
-    graphs.run({1, B, T, (int)((uintptr_t)audio & 0x7fffffff), (int)((uintptr_t)audio >> 31), (int)((uintptr_t)z & 0x7fffffff),
-                (int)((uintptr_t)z >> 31)},
-               st, [&] { decode_body(z, audio, B, T, st); });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_z, z, (size_t)B * cfg.ae_z_channels * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    graphs.run({1, B, T}, st, [&] { decode_body(io_z, io_audio, B, T, st); });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(audio, io_audio, (size_t)B * T * ratio * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
 };
 
