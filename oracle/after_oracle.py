@@ -77,11 +77,40 @@ def rope_rotate(x: Tensor, rot_dim: int = 32, theta: float = 10000.0, offset: in
     return torch.cat([rot, x[..., rot_dim:]], dim=-1)
 
 
+class StreamCache:
+    """Rolling per-(layer, diffusion step) key/value history of the streaming denoiser:
+    ``MHAttention.k_cache / v_cache`` of shape (max_batch, max_steps, H, cache, dh), zero-initialised
+    (so the first blocks really attend to all-zero keys/values), plus the un-rotated k/v of the last
+    forward (``last_k / last_v``); transformerv2.py:143-188."""
+
+    def __init__(self, cfg, cache_size: int, max_batch: int = 4, max_steps: int = 16, dtype=torch.float32):
+        shape = (max_batch, max_steps, cfg.n_heads, cache_size, cfg.head_dim)
+        self.cache_size = cache_size
+        self.k = [torch.zeros(shape, dtype=dtype) for _ in range(cfg.n_layers)]
+        self.v = [torch.zeros(shape, dtype=dtype) for _ in range(cfg.n_layers)]
+        self.last_k = [None] * cfg.n_layers
+        self.last_v = [None] * cfg.n_layers
+
+    def roll(self, roll_size: int, cache_index: int) -> None:
+        """``DenoiserV2.roll_cache``: append the first ``roll_size`` frames of the last block, keep the newest
+        ``cache_size``; transformerv2.py:167-186."""
+        for l in range(len(self.k)):
+            lk, lv = self.last_k[l], self.last_v[l]
+            n = lk.shape[0]
+            k = torch.cat([self.k[l][:n, cache_index], lk[:, :, :roll_size]], dim=2)[:, :, -self.cache_size:]
+            v = torch.cat([self.v[l][:n, cache_index], lv[:, :, :roll_size]], dim=2)[:, :, -self.cache_size:]
+            self.k[l][:n, cache_index] = k
+            self.v[l][:n, cache_index] = v
+
+
 def denoiser_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Tensor,
-                     time_cond: Tensor, taps: Optional[dict] = None) -> Tensor:
-    """``DenoiserV2.forward`` offline path (max_cache_size = 0); transformerv2.py:517-543,
-    437-457, 340-362, 190-236.  x (N,C,T), time (N,)|(N,1,1)|(N,1,T), cond (N,zt),
-    time_cond (N,zs,T) -> (N,C,T)."""
+                     time_cond: Tensor, taps: Optional[dict] = None, cache: Optional[StreamCache] = None,
+                     cache_index: int = 0) -> Tensor:
+    """``DenoiserV2.forward``; transformerv2.py:517-543, 437-457, 340-362, 190-236.  x (N,C,T),
+    time (N,)|(N,1,1)|(N,1,T), cond (N,zt), time_cond (N,zs,T) -> (N,C,T).  ``cache`` = None is the offline
+    path (max_cache_size = 0); with a ``StreamCache`` the keys/values of the block are appended to the cached
+    history of ``cache_index`` (keys are cached UN-rotated; queries are rotated at offset = history length,
+    rotary_embedding.py:215-236) and the band mask is the last T rows of the mask over history + block."""
     dt = x.dtype
     sd = _cast(sd, dt)
     D, H, dh = cfg.embed_dim, cfg.n_heads, cfg.head_dim
@@ -105,8 +134,9 @@ def denoiser_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Tensor,
         F.linear(time_cond.transpose(1, 2), sd[tb + "patchify_and_embed_tcond.1.weight"],
                  sd[tb + "patchify_and_embed_tcond.1.bias"]))  # (N, T, zs)
 
-    allowed = band_allowed(T, cfg.attention_chunk_size, cfg.local_attention_size)
-    bias = torch.zeros(T, T, dtype=dt).masked_fill(~allowed, float("-inf"))
+    hist = cache.cache_size if cache is not None else 0
+    allowed = band_allowed(hist + T, cfg.attention_chunk_size, cfg.local_attention_size)[hist:]
+    bias = torch.zeros(T, hist + T, dtype=dt).masked_fill(~allowed, float("-inf"))
     if taps is not None:
         taps["features"] = feat
         taps["h0"] = h
@@ -120,7 +150,11 @@ def denoiser_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Tensor,
         y = F.layer_norm(h, (D, ), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
         q, k, v = F.linear(y, sd[p + "self_attention.qkv_linear.weight"]).chunk(3, dim=2)
         q, k, v = (z.reshape(N, T, H, dh).transpose(1, 2) for z in (q, k, v))
-        q = rope_rotate(q, cfg.rotary_dim, cfg.rotary_theta)
+        if cache is not None:
+            cache.last_k[i], cache.last_v[i] = k, v
+            k = torch.cat([cache.k[i][:N, cache_index].to(dt), k], dim=2)
+            v = torch.cat([cache.v[i][:N, cache_index].to(dt), v], dim=2)
+        q = rope_rotate(q, cfg.rotary_dim, cfg.rotary_theta, offset=hist)
         k = rope_rotate(k, cfg.rotary_dim, cfg.rotary_theta)
         s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh) + bias
         a = torch.matmul(torch.softmax(s, dim=-1), v)
@@ -148,7 +182,7 @@ CFG_MIDI = 1  # rows: (cond, tc) / (cond, drop) / (drop, drop); factor = g_s / m
 
 def model_forward(sd, cfg, x, time, cond, time_cond, guidance_timbre: float,
                   guidance_structure: float, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
-                  clamp: float = 0.01) -> Tensor:
+                  clamp: float = 0.01, cache: Optional[StreamCache] = None, cache_index: int = 0) -> Tensor:
     """3-way classifier-free-guidance evaluation; model.py:721-761 (audio variant) and
     after_scripts/export_midi.py:322-360 (midi variant, clamp 0.1)."""
     B = x.shape[0]
@@ -164,7 +198,7 @@ def model_forward(sd, cfg, x, time, cond, time_cond, guidance_timbre: float,
         tconds = torch.cat([time_cond, drop_t, drop_t])
         g_first, g_second = guidance_structure, guidance_timbre
     t = time.reshape(B, -1)[:, 0]
-    d = denoiser_forward(sd, cfg, x[idx], t[idx], conds, tconds)
+    d = denoiser_forward(sd, cfg, x[idx], t[idx], conds, tconds, cache=cache, cache_index=cache_index)
     d_full, d_mid, d_none = d[:B], d[B:2 * B], d[2 * B:]
     total = 0.5 * (guidance_structure + guidance_timbre)
     factor = g_first / max(g_second, clamp)
@@ -184,6 +218,24 @@ def sample(sd, cfg, x0, cond, time_cond, nb_steps: int, guidance_timbre: float =
         tt = t.to(x.dtype).reshape(1).repeat(B)
         x = x + model_forward(sd, cfg, x, tt, cond, time_cond, guidance_timbre,
                               guidance_structure, drop_value, cfg_variant, clamp) * dt
+    return x
+
+
+@torch.no_grad()
+def sample_stream(sd, cfg, cache: StreamCache, x_last, cond, time_cond, nb_steps: int, guidance_timbre: float = 1.0,
+                  guidance_structure: float = 1.0, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
+                  clamp: float = 0.1) -> Tensor:
+    """One audio block of the exported ``Streamer.sample``: Euler step i runs against KV cache i, which is then
+    rolled by the block length; after_scripts/export.py:356-416 (guidance ratio clamped at 0.1, :389-390)."""
+    x = x_last
+    B = x.shape[0]
+    ts = torch.linspace(0, 1, nb_steps + 1)[:-1]
+    dt = 1 / nb_steps
+    for i, t in enumerate(ts):
+        tt = t.to(x.dtype).reshape(1).repeat(B)
+        x = x + model_forward(sd, cfg, x, tt, cond, time_cond, guidance_timbre, guidance_structure, drop_value,
+                              cfg_variant, clamp, cache=cache, cache_index=i) * dt
+        cache.roll(x.shape[-1], i)
     return x
 
 

@@ -110,3 +110,37 @@ def test_codec_roundtrip_length():
     z = O.ae_encode(sd, acfg, x)
     assert z.shape == (3, acfg.z_channels, 8192 // acfg.ratio)
     assert O.ae_decode(sd, acfg, z).shape == x.shape
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# streaming path (per-diffusion-step rolling KV caches), fixtures from tests/golden/make_golden_stream.py
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,name", [("tiny", "tiny"), ("tiny_t8", "tiny"), ("base", "base"), ("midi", "midi")])
+def test_stream_denoiser_matches_reference(golden, tag, name):
+    g = golden(f"stream_denoiser_{tag}")
+    cfg = config.get_config(name).denoiser
+    sd = synth.denoiser_state_dict(cfg, int(g["weight_seed"]))
+    cache = O.StreamCache(cfg, int(g["cache_size"]))
+    worst = 0.0
+    for b in range(g["x"].shape[0]):
+        ci = int(g["cache_index"][b])
+        out = O.denoiser_forward(sd, cfg, T(g["x"][b]), T(g["time"][b]), T(g["cond"][b]), T(g["time_cond"][b]),
+                                 cache=cache, cache_index=ci)
+        cache.roll(int(g["roll"]), ci)
+        worst = max(worst, rel(out, g["out"][b]))
+    assert worst < 1e-5, worst
+    # the history matters: the offline forward of the last block differs from its streaming output
+    off = O.denoiser_forward(sd, cfg, T(g["x"][-1]), T(g["time"][-1]), T(g["cond"][-1]), T(g["time_cond"][-1]))
+    assert rel(off, g["out"][-1]) > 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny", "base"])
+def test_stream_sample_matches_reference(golden, name):
+    g = golden(f"stream_sample_{name}")
+    cfg = config.get_config(name).denoiser
+    sd = synth.denoiser_state_dict(cfg, int(g["weight_seed"]))
+    cache = O.StreamCache(cfg, int(g["cache_size"]))
+    for b in range(g["x0"].shape[0]):
+        out = O.sample_stream(sd, cfg, cache, T(g["x0"][b]), T(g["cond"][b]), T(g["time_cond"][b]), int(g["nb_steps"]),
+                              float(g["guidance_timbre"]), float(g["guidance_structure"]))
+        assert rel(out, g["out"][b]) < 2e-5, (b, rel(out, g["out"][b]))
