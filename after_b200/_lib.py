@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libafter_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_STAGES = 8
 
 OK, IGNORED = 0, 1
@@ -68,6 +68,7 @@ class AfterConfig(C.Structure):
         ("te_out_dim", C.c_int32),
         ("te_global_context", C.c_int32),
         ("te_use_tanh", C.c_int32),
+        ("max_cache_size", C.c_int32),
     ]
 
 
@@ -91,6 +92,14 @@ PROTOTYPES = {
                                C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "after_sample_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "after_denoiser_forward_cached": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p]),
+    "after_model_forward_cached": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "after_roll_cache": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "after_reset_cache": (C.c_int, [_H, C.c_void_p]),
+    "after_sample_stream": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "after_ae_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "after_ae_decode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_structure_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

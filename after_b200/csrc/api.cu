@@ -100,7 +100,7 @@ extern "C" {
 int after_abi_version(void) { return AFTER_B200_ABI_VERSION; }
 
 const char* after_build_info(void) {
-  return "libafter_b200 abi=1 arch=sm_100a (tcgen05/TMEM/TMA) nvcc=" AFTER_STR(__CUDACC_VER_MAJOR__) "." AFTER_STR(
+  return "libafter_b200 abi=2 arch=sm_100a (tcgen05/TMEM/TMA) nvcc=" AFTER_STR(__CUDACC_VER_MAJOR__) "." AFTER_STR(
       __CUDACC_VER_MINOR__) " built " __DATE__;
 }
 
@@ -266,6 +266,73 @@ int after_sample(after_handle h, const float* x0, const float* cond, const float
     h->bridge.enter(user);
     h->denoiser.sample(x0, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
                        h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_denoiser_forward_cached(after_handle h, const float* x, const float* time, const float* cond,
+                                  const float* time_cond, float* out, int N, int T, int cache_index, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    h->denoiser.check_cache_index(cache_index);
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.forward(x, time, cond, time_cond, out, N, T, h->bridge.work, cache_index);
+    h->bridge.exit(user);
+  });
+}
+
+int after_model_forward_cached(after_handle h, const float* x, const float* time, const float* cond,
+                               const float* time_cond, float* out, int B, int T, float guidance_timbre,
+                               float guidance_structure, int cfg_variant, float clamp, int cache_index, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    h->denoiser.check_cache_index(cache_index);
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.model_forward(x, time, cond, time_cond, out, B, T, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                              h->bridge.work, cache_index);
+    h->bridge.exit(user);
+  });
+}
+
+int after_roll_cache(after_handle h, int roll_size, int cache_index, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.roll_cache(roll_size, cache_index, h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_reset_cache(after_handle h, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.reset_cache(h->bridge.work);
+    h->bridge.exit(user);
+  });
+}
+
+int after_sample_stream(after_handle h, const float* x_last, const float* cond, const float* time_cond, float* out, int B,
+                        int T, int nb_steps, float guidance_timbre, float guidance_structure, int cfg_variant, float clamp,
+                        void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
+    AFTER_REQUIRE(x_last && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    h->bridge.enter(user);
+    h->denoiser.sample(x_last, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                       h->bridge.work, /*stream=*/true);
     h->bridge.exit(user);
   });
 }

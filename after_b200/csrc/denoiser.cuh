@@ -42,12 +42,21 @@ struct Denoiser {
   // workspace
   float *x_state, *x_in, *cond_buf, *tc_buf, *time_buf;
   float *h0, *h, *qkv, *proj;
+  float* h_part = nullptr;  // second K half of a K-split down projection (added by the next layer's AdaLN-t kernel)
   ActOperand a_op, hid_op;  // GEMM A operands: LN output [rows, D], MLP hidden [rows, HID]
   float *tcemb, *adaT, *E, *F1, *feat, *adaC;
   int *map_src, *map_trow, *map_tstride, *map_crow;
   float* guidance;
   int* mlp_flags = nullptr;  // fused-MLP dependency counters: [L][row blocks]
   int flag_stride = 0;
+
+  // streaming state (transformerv2.py:143-188): un-rotated key/value history per (diffusion step, layer, sequence),
+  // zero-initialised like the reference's registered buffers, plus the q|k|v of the last cached forward of every layer
+  // (the reference's last_k / last_v) which roll_cache appends.
+  int cacheW = 0;                               // after_config.max_cache_size; 0 = offline only
+  float *kcache = nullptr, *vcache = nullptr;   // [max_steps][L][maxN][cacheW][D]
+  float* qkv_stream = nullptr;                  // [L][maxRows][3D]
+  int last_N = 0, last_T = 0;
 
   // graph cache
   struct GraphEntry {
@@ -134,8 +143,9 @@ struct Denoiser {
       else
         for (int j = 0; j < half; ++j) inv[j] = 1.0f / powf(10000.0f, (float)(2 * j) / 32.0f);
       rope_inv = arena->upload(inv);
-      rope_tab = arena->alloc<float2>((size_t)maxT * half);
-      rope_table_kernel<<<ceil_div(maxT * half, 256), 256>>>(rope_tab, rope_inv, maxT, half);
+      const int npos = maxT + std::max(0, (int)c.max_cache_size);  // streaming: positions run over history + block
+      rope_tab = arena->alloc<float2>((size_t)npos * half);
+      rope_table_kernel<<<ceil_div(npos * half, 256), 256>>>(rope_tab, rope_inv, npos, half);
       AFTER_CUDA_CHECK(cudaGetLastError());
       // fourier frequencies (1/max_positions)^(k/half) as fp32 (transformerv2.py:34-40)
       const int fh = NE / 2;
@@ -152,6 +162,7 @@ struct Denoiser {
     time_buf = arena->alloc<float>((size_t)std::max(maxN, c.max_steps));
     h0 = arena->alloc<float>((size_t)maxRows * D);
     h = arena->alloc<float>((size_t)maxRows * D);
+    h_part = arena->alloc<float>((size_t)maxRows * D);
     qkv = arena->alloc<float>((size_t)maxRows * 3 * D);
     proj = arena->alloc<float>((size_t)maxRows * C);
     alloc_operand(a_op, *arena, (size_t)maxRows * D, tc_mode(), false);
@@ -168,6 +179,16 @@ struct Denoiser {
     guidance = arena->alloc<float>(4);
     flag_stride = maxN * ceil_div(maxT, 2 * tc::BM);
     mlp_flags = arena->alloc<int>((size_t)L * flag_stride);
+    cacheW = c.max_cache_size;
+    AFTER_REQUIRE(cacheW >= 0 && cacheW <= 64, AFTER_EINVAL, "max_cache_size must be in [0, 64]");
+    if (cacheW > 0) {
+      const size_t cache_floats = (size_t)c.max_steps * L * maxN * cacheW * D;
+      kcache = arena->alloc<float>(cache_floats);
+      vcache = arena->alloc<float>(cache_floats);
+      qkv_stream = arena->alloc<float>((size_t)L * maxRows * 3 * D);
+      AFTER_CUDA_CHECK(cudaMemset(kcache, 0, cache_floats * sizeof(float)));
+      AFTER_CUDA_CHECK(cudaMemset(vcache, 0, cache_floats * sizeof(float)));
+    }
     const char* ng = getenv("AFTER_NO_GRAPH");
     use_graph = !(ng && ng[0] == '1');
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
@@ -226,12 +247,12 @@ struct Denoiser {
   }
 
   template <int NV>
-  void launch_adaln_t(const float* hin, int use_src, int l, int rows, int T, cudaStream_t st) {
+  void launch_adaln_t(const float* hin, const float* hadd, int use_src, int l, int rows, int T, cudaStream_t st) {
     RowOperandOut o = operand_out(a_op);
     ProfScope prof(KC_ROW_NORM, st, 0.0, (double)rows * D * (tc_mode() ? 4.0 * 2 + 2.0 * (nprod() > 1 ? 2 : 1) : 12.0));
-    adaln_t_ln1_kernel<NV><<<ceil_div(rows, 8), 256, 0, st>>>(hin, h, o, adaT, L * 2 * D, l * 2 * D, seqmap(), use_src,
-                                                             layers[l].n1_g, layers[l].n1_b, rows, T);
-    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    launch_k(adaln_t_ln1_kernel<NV>, dim3(ceil_div(rows, 8)), dim3(256), 0, st, hin, hadd, h, o, adaT, L * 2 * D, l * 2 * D, seqmap(),
+             use_src, layers[l].n1_g, layers[l].n1_b, rows, T);
+    AFTER_COUNT_LAUNCH();
   }
   template <int NH, int MAXK>
   void launch_attn(int l, const float* adaC_step, int rows, int T, cudaStream_t st) {
@@ -241,15 +262,15 @@ struct Denoiser {
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
     if (cfg.attention_chunk_size == 4) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      attn_chunk4_kernel<NH, MAXK><<<chunks, NH * 32, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
-                                                                        layers[l].n3_g, layers[l].n3_b, n_seq, T,
-                                                                        cfg.local_attention_size);
+      launch_k(attn_chunk4_kernel<NH, MAXK>, dim3(chunks), dim3(NH * 32), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
+               seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
+               mlp_flags + (size_t)l * flag_stride, flag_stride);
     } else {
-      attn_adaln_c_ln3_kernel<NH, MAXK><<<ceil_div(rows, 4), 128, 0, st>>>(qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(),
-                                                                           layers[l].n3_g, layers[l].n3_b, rows, T,
-                                                                           cfg.attention_chunk_size, cfg.local_attention_size);
+      launch_k(attn_adaln_c_ln3_kernel<NH, MAXK>, dim3(ceil_div(rows, 4)), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D,
+               l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, rows, T, cfg.attention_chunk_size,
+               cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride, flag_stride);
     }
-    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    AFTER_COUNT_LAUNCH();
   }
   void attn(int l, const float* adaC_step, int rows, int T, cudaStream_t st) {
     const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
@@ -264,24 +285,89 @@ struct Denoiser {
     }
   }
 
+  // ---- streaming (cached) attention: history rows come from the cache of (cache_index, layer), RoPE is applied on the fly
+  size_t cache_slab() const { return (size_t)L * maxN * cacheW * D; }  // floats per diffusion step
+  template <int NH, int MAXK>
+  void launch_attn_stream(int l, int cache_index, const float* adaC_step, int rows, int T, cudaStream_t st) {
+    RowOperandOut o = operand_out(a_op);
+    ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
+                   (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
+    const size_t off = (size_t)cache_index * cache_slab() + (size_t)l * maxN * cacheW * D;
+    launch_k(attn_stream_kernel<NH, MAXK>, dim3(ceil_div(rows, 4)), dim3(128), 0, st, qkv_stream + (size_t)l * maxRows * 3 * D,
+             kcache + off, vcache + off, cacheW, rope_tab, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g,
+             layers[l].n3_b, rows, T, cfg.attention_chunk_size, cfg.local_attention_size,
+             mlp_flags + (size_t)l * flag_stride, flag_stride);
+    AFTER_COUNT_LAUNCH();
+  }
+  void attn_stream(int l, int cache_index, const float* adaC_step, int rows, int T, cudaStream_t st) {
+    const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
+    if (H == 8) {
+      if (mk <= 12) launch_attn_stream<8, 12>(l, cache_index, adaC_step, rows, T, st);
+      else if (mk <= 20) launch_attn_stream<8, 20>(l, cache_index, adaC_step, rows, T, st);
+      else launch_attn_stream<8, 32>(l, cache_index, adaC_step, rows, T, st);
+    } else {
+      if (mk <= 12) launch_attn_stream<4, 12>(l, cache_index, adaC_step, rows, T, st);
+      else if (mk <= 20) launch_attn_stream<4, 20>(l, cache_index, adaC_step, rows, T, st);
+      else launch_attn_stream<4, 32>(l, cache_index, adaC_step, rows, T, st);
+    }
+  }
+
+  // DenoiserV2.roll_cache (transformerv2.py:167-186, 433-435): every layer's history of `cache_index` takes the first
+  // min(roll_size, T_last) frames of the last cached forward and keeps the newest cacheW.
+  void roll_cache(int roll_size, int cache_index, cudaStream_t st) {
+    AFTER_REQUIRE(cacheW > 0, AFTER_ESTATE, "this handle was created with max_cache_size == 0 (offline only)");
+    AFTER_REQUIRE(cache_index >= 0 && cache_index < cfg.max_steps, AFTER_EINVAL, "cache_index must be in [0, max_steps)");
+    AFTER_REQUIRE(roll_size >= 0, AFTER_EINVAL, "roll_size must be >= 0");
+    AFTER_REQUIRE(last_N > 0, AFTER_ESTATE, "roll_cache before any cached forward");
+    const int r = std::min(roll_size, last_T);
+    if (r == 0) return;
+    const size_t off = (size_t)cache_index * cache_slab();
+    dim3 grid(L, last_N, 2);
+    PdlScope pdl(true);
+    launch_k(kv_roll_kernel, grid, dim3(256), 0, st, kcache + off, vcache + off, qkv_stream, maxN, maxRows, last_T, cacheW, r, D);
+    AFTER_COUNT_LAUNCH();
+  }
+
+  void reset_cache(cudaStream_t st) {
+    AFTER_REQUIRE(cacheW > 0, AFTER_ESTATE, "this handle was created with max_cache_size == 0 (offline only)");
+    const size_t bytes = (size_t)cfg.max_steps * cache_slab() * sizeof(float);
+    AFTER_CUDA_CHECK(cudaMemsetAsync(kcache, 0, bytes, st));
+    AFTER_CUDA_CHECK(cudaMemsetAsync(vcache, 0, bytes, st));
+    last_N = last_T = 0;
+  }
+
+  void check_cache_index(int cache_index) {
+    AFTER_REQUIRE(cacheW > 0, AFTER_ESTATE, "this handle was created with max_cache_size == 0 (offline only)");
+    AFTER_REQUIRE(cache_index >= 0 && cache_index < cfg.max_steps, AFTER_EINVAL, "cache_index must be in [0, max_steps)");
+  }
+
   // One network evaluation: x_src (n_src, C, T) channel-first -> proj [N*T, C] token-major.
-  void run_network(const float* x_src, int n_src, int N, int T, const float* adaC_step, cudaStream_t st) {
+  // cache_index >= 0 selects the streaming attention (history of that diffusion step + this block).
+  void run_network(const float* x_src, int n_src, int N, int T, const float* adaC_step, cudaStream_t st,
+                   int cache_index = -1) {
     const int rows = N * T;
-    AFTER_CUDA_CHECK(cudaMemsetAsync(mlp_flags, 0, (size_t)L * flag_stride * sizeof(int), st));
+    PdlScope pdl(true);  // every kernel below starts with pdl_wait(): programmatic dependent launches are safe
     {
       dim3 grid(ceil_div(T, 4), n_src);
-      patch_embed_kernel<4><<<grid, 256, C * 4 * sizeof(float), st>>>(x_src, pe_wt, pe_b, h0, C, T, D);
-      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+      launch_k(patch_embed_kernel<4>, grid, dim3(256), C * 4 * sizeof(float), st, x_src, pe_wt, pe_b, h0, C, T, D);
+      AFTER_COUNT_LAUNCH();
     }
+    bool part = false;  // previous layer's down projection left its second K half in h_part
     for (int l = 0; l < L; ++l) {
       const float* hin = l == 0 ? h0 : h;
-      if (D == 512) launch_adaln_t<16>(hin, l == 0, l, rows, T, st);
-      else launch_adaln_t<8>(hin, l == 0, l, rows, T, st);
-      {
+      const float* hadd = part ? h_part : nullptr;
+      if (D == 512) launch_adaln_t<16>(hin, hadd, l == 0, l, rows, T, st);
+      else launch_adaln_t<8>(hin, hadd, l == 0, l, rows, T, st);
+      part = false;
+      if (cache_index < 0) {
         GemmEpi e; e.out_f32 = qkv; e.ldo = 3 * D; e.rope = 1; e.D = D; e.rot_half = 16; e.rope_tab = rope_tab;
         gemm(layers[l].qkv, a_op, N, T, e, st);
+        attn(l, adaC_step, rows, T, st);
+      } else {  // keys are cached un-rotated: plain epilogue into this layer's slot, rotation inside the attention kernel
+        GemmEpi e; e.out_f32 = qkv_stream + (size_t)l * maxRows * 3 * D; e.ldo = 3 * D;
+        gemm(layers[l].qkv, a_op, N, T, e, st);
+        attn_stream(l, cache_index, adaC_step, rows, T, st);
       }
-      attn(l, adaC_step, rows, T, st);
       {
         GemmEpi e0; e0.ldo = HID; e0.gelu = 1;
         e0.out_f32 = hid_op.f32; e0.out_hi = hid_op.hi; e0.out_lo = nprod() > 1 ? hid_op.lo : nullptr;
@@ -289,7 +375,8 @@ struct Denoiser {
         if (l == L - 1 && tc_mode()) { e1.out_hi = a_op.hi; e1.out_lo = nprod() > 1 ? a_op.lo : nullptr; }
         // one persistent launch for both MLP projections when the shapes allow it, else two launches
         int* fl = mlp_flags + (size_t)l * flag_stride;
-        if (!(tc_mode() && launch_mlp_fused(a_op, layers[l].mlp0, e0, hid_op, layers[l].mlp2, e1, N, T, precision, fl, st))) {
+        if (!(tc_mode() && launch_mlp_fused(a_op, layers[l].mlp0, e0, hid_op, layers[l].mlp2, e1, N, T, precision, fl, st,
+                                            l < L - 1 ? h_part : nullptr, &part))) {
           gemm(layers[l].mlp0, a_op, N, T, e0, st);
           gemm(layers[l].mlp2, hid_op, N, T, e1, st);
         }
@@ -304,6 +391,7 @@ struct Denoiser {
         gemm(out_proj, a_op, N, T, e, st);
       }
     }
+    if (cache_index >= 0) { last_N = N; last_T = T; }
   }
 
   void upload_maps(const std::vector<int>& src, const std::vector<int>& trow, const std::vector<int>& tstr,
@@ -323,8 +411,9 @@ struct Denoiser {
 
   // ------------------------------------------------------------------ DenoiserV2.forward
   void forward(const float* x, const float* time, const float* cond, const float* time_cond, float* out, int N, int T,
-               cudaStream_t st) {
+               cudaStream_t st, int cache_index = -1) {
     check_shape(N, T);
+    if (cache_index >= 0) check_cache_index(cache_index);
     AFTER_CUDA_CHECK(cudaMemcpyAsync(cond_buf, cond, (size_t)N * zt * 4, cudaMemcpyDeviceToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(tc_buf, time_cond, (size_t)N * zs * T * 4, cudaMemcpyDeviceToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(time_buf, time, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
@@ -332,7 +421,7 @@ struct Denoiser {
     for (int n = 0; n < N; ++n) { src[n] = n; trow[n] = n * T; crow[n] = n; }
     upload_maps(src, trow, tstr, crow, st);
     build_tables(N, T, N, 1, N, N, st);
-    run_network(x, N, N, T, adaC, st);
+    run_network(x, N, N, T, adaC, st, cache_index);
     dim3 grid(ceil_div(T, 32), ceil_div(C, 32), N);
     tokens_to_channels_kernel<<<grid, 256, 0, st>>>(proj, out, C, T);
     AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
@@ -366,14 +455,16 @@ struct Denoiser {
 
   void combine(int B, int T, const float* xin, float* xout, int euler, cudaStream_t st) {
     dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B);
-    cfg_combine_kernel<<<grid, 256, 0, st>>>(proj, guidance, xin, xout, B, C, T, euler);
-    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    PdlScope pdl(true);
+    launch_k(cfg_combine_kernel, grid, dim3(256), 0, st, proj, guidance, xin, xout, B, C, T, euler);
+    AFTER_COUNT_LAUNCH();
   }
 
   // ------------------------------------------------------------------ RectifiedFlow.model_forward
   void model_forward(const float* x, const float* time, const float* cond, const float* time_cond, float* out, int B,
-                     int T, float g_t, float g_s, int variant, float clamp, cudaStream_t st) {
+                     int T, float g_t, float g_s, int variant, float clamp, cudaStream_t st, int cache_index = -1) {
     check_shape(3 * B, T);
+    if (cache_index >= 0) check_cache_index(cache_index);
     AFTER_REQUIRE(variant == AFTER_CFG_AUDIO || variant == AFTER_CFG_MIDI, AFTER_EINVAL, "unknown cfg_variant");
     AFTER_CUDA_CHECK(cudaMemcpyAsync(cond_buf, cond, (size_t)B * zt * 4, cudaMemcpyDeviceToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(tc_buf, time_cond, (size_t)B * zs * T * 4, cudaMemcpyDeviceToDevice, st));
@@ -383,7 +474,7 @@ struct Denoiser {
     model_forward_tables(time, B, T, st);
     cfg_maps_per_stream(B, T, variant, st);
     set_guidance(g_t, g_s, variant, clamp, 1.0f, st);
-    run_network(x, B, 3 * B, T, adaC, st);
+    run_network(x, B, 3 * B, T, adaC, st, cache_index);
     combine(B, T, x, out, 0, st);
   }
 
@@ -423,18 +514,22 @@ struct Denoiser {
     return t;
   }
 
-  void sample_body(int B, int T, int nb_steps, cudaStream_t st) {
+  // stream = true is one audio block of the exported Streamer.sample (after_scripts/export.py:398-416): Euler step s runs
+  // against KV cache s, which is then rolled by the block length.
+  void sample_body(int B, int T, int nb_steps, cudaStream_t st, bool stream = false) {
     build_tables(B, T, nb_steps * (B + 1), 0, B, B + 1, st);
     const size_t step_stride = (size_t)(B + 1) * L * 2 * D;
     for (int s = 0; s < nb_steps; ++s) {
-      run_network(x_state, B, 3 * B, T, adaC + (size_t)s * step_stride, st);
+      run_network(x_state, B, 3 * B, T, adaC + (size_t)s * step_stride, st, stream ? s : -1);
       combine(B, T, x_state, x_state, 1, st);
+      if (stream) roll_cache(T, s, st);
     }
   }
 
   void sample(const float* x0, const float* cond, const float* time_cond, float* out, int B, int T, int nb_steps,
-              float g_t, float g_s, int variant, float clamp, cudaStream_t st) {
+              float g_t, float g_s, int variant, float clamp, cudaStream_t st, bool stream = false) {
     check_shape(3 * B, T);
+    if (stream) check_cache_index(0);
     AFTER_REQUIRE(nb_steps >= 1 && nb_steps <= cfg.max_steps, AFTER_EINVAL, "nb_steps exceeds max_steps given at after_create");
     AFTER_REQUIRE(variant == AFTER_CFG_AUDIO || variant == AFTER_CFG_MIDI, AFTER_EINVAL, "unknown cfg_variant");
     const size_t xb = (size_t)B * C * T * 4;
@@ -447,9 +542,9 @@ struct Denoiser {
     set_guidance(g_t, g_s, variant, clamp, 1.0f / (float)nb_steps, st);
 
     if (!use_graph || g_prof.on) {
-      sample_body(B, T, nb_steps, st);
+      sample_body(B, T, nb_steps, st, stream);
     } else {
-      auto key = std::make_tuple(B, T, nb_steps, variant, 0);
+      auto key = std::make_tuple(B, T, nb_steps, variant, stream ? 1 : 0);
       auto it = graphs.find(key);
       if (it == graphs.end()) {
         GraphEntry ge;
@@ -457,7 +552,7 @@ struct Denoiser {
         const int64_t before = g_launches.load();
         AFTER_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
-          sample_body(B, T, nb_steps, st);
+          sample_body(B, T, nb_steps, st, stream);
         } catch (...) {
           cudaStreamEndCapture(st, &graph);
           if (graph) cudaGraphDestroy(graph);
@@ -472,6 +567,7 @@ struct Denoiser {
       }
       AFTER_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
       g_launches.fetch_add(it->second.kernels);
+      if (stream) { last_N = 3 * B; last_T = T; }
     }
     AFTER_CUDA_CHECK(cudaMemcpyAsync(out, x_state, xb, cudaMemcpyDeviceToDevice, st));
   }

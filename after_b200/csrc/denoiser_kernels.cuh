@@ -50,15 +50,17 @@ struct SeqMap {
 };
 
 // -------------------------------------------------------------------------------------------
-// h <- LN0(h) * (1 + alpha_t) + beta_t ;  a <- LN1(h) * g1 + b1            (transformerv2.py:345-351)
+// h <- LN0(h [+ h_add]) * (1 + alpha_t) + beta_t ;  a <- LN1(h) * g1 + b1   (transformerv2.py:345-351)
 // lane layout: lane owns float4 groups  e = (i*32 + lane)*4 .. +3,  i < NV/4
 // -------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256)
-adaln_t_ln1_kernel(const float* h_in, float* h_out, RowOperandOut a_out,
+adaln_t_ln1_kernel(const float* h_in, const float* h_add, float* h_out, RowOperandOut a_out,
                    const float* __restrict__ adaT, int ada_ld, int ada_off, SeqMap map, int use_src,
                    const float* __restrict__ g1, const float* __restrict__ b1, int n_rows, int T) {
   constexpr int D = NV * 32;
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -72,6 +74,14 @@ adaln_t_ln1_kernel(const float* h_in, float* h_out, RowOperandOut a_out,
   for (int i = 0; i < NV / 4; ++i) {
     float4 v = *reinterpret_cast<const float4*>(hp + (i * 32 + lane) * 4);
     x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  if (h_add) {  // second K half of the previous layer's down projection (LinearProblem::ksplit), same row layout
+    const float* pp = h_add + (size_t)src_row * D;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(pp + (i * 32 + lane) * 4);
+      x[4 * i] += v.x; x[4 * i + 1] += v.y; x[4 * i + 2] += v.z; x[4 * i + 3] += v.w;
+    }
   }
   float mean, rstd;
   row_stats<NV>(x, D, mean, rstd);
@@ -117,7 +127,12 @@ template <int NH, int MAXK>
 __global__ void __launch_bounds__(NH * 32, 32 / NH)
 attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
                    const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
-                   const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window) {
+                   const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
+                   int* zero_flags, int n_zero) {
+  pdl_wait();
+  pdl_trigger();
+  // the fused MLP of this layer (next kernel) counts finished up-projection tiles per row block in zero_flags
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
   // Block = one attention chunk (4 queries), warp = head: NH warps x 1536 chunks keeps ~64 warps resident per SM, which
   // is what hides the L2 round trips of the key/value rows (the kernel is latency-, not bandwidth-bound).
   // Phase 1 (all warps): lane = (query qi = lane >> 3, dsub = lane & 7) owns dims [4 dsub, +4) and [32 + 4 dsub, +4) of
@@ -243,8 +258,11 @@ __global__ void __launch_bounds__(128)
 attn_adaln_c_ln3_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
                         const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
                         const float* __restrict__ g3, const float* __restrict__ b3, int n_rows, int T,
-                        int chunk, int window) {
+                        int chunk, int window, int* zero_flags, int n_zero) {
   constexpr int D = NH * 64;
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -326,6 +344,137 @@ attn_adaln_c_ln3_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
 }
 
 // -------------------------------------------------------------------------------------------
+// Streaming attention (transformerv2.py:190-236 with max_cache_size = W > 0, rotary_embedding.py:215-236):
+// the key/value sequence of block frame t is [history (W cached frames) ; block (T frames)], the query sits at
+// position p = W + t of it, the band is the same index arithmetic over that longer sequence, and RoPE is applied
+// here (queries at p, keys at their position in history + block) because the history is cached UN-rotated and
+// every roll shifts its positions.  qkv holds the plain projection of this block; kc / vc: [n][W][D] of this
+// (diffusion step, layer).  Same warp-per-token layout and same tail (residual, AdaLN-c, LN3) as the kernel above;
+// lanes 0..15 own exactly the 16 interleaved rotary pairs of each head (dims 2 lane, 2 lane + 1 < 32).
+// -------------------------------------------------------------------------------------------
+template <int NH, int MAXK>
+__global__ void __launch_bounds__(128)
+attn_stream_kernel(const float* __restrict__ qkv, const float* __restrict__ kc, const float* __restrict__ vc, int W,
+                   const float2* __restrict__ rope_tab, float* h, RowOperandOut a_out,
+                   const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
+                   const float* __restrict__ g3, const float* __restrict__ b3, int n_rows, int T, int chunk, int window,
+                   int* zero_flags, int n_zero) {
+  constexpr int D = NH * 64;
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int n = row / T, t = row - n * T;
+  const int p = W + t, Lk = W + T;
+  const int c0 = (p / chunk) * chunk;
+  const int ce = min(c0 + chunk, Lk);
+  const int ks = min(c0, max(0, p - window + 1));
+  const int nk = ce - ks;  // <= chunk + window - 1 <= MAXK
+  const float* qrow = qkv + (size_t)row * (3 * D);
+  const float* kcn = kc + (size_t)n * W * D;
+  const float* vcn = vc + (size_t)n * W * D;
+  const float* kblk = qkv + (size_t)n * T * (3 * D) + D;  // block frame j: kblk + j * 3D ; value: + D more
+  const bool rot = lane < 16;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  float2 cq = make_float2(1.f, 0.f);
+  if (rot) cq = rope_tab[p * 16 + lane];
+
+  float x[NH * 2];
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    float2 q = *reinterpret_cast<const float2*>(qrow + hd * 64 + 2 * lane);
+    q = make_float2(q.x * cq.x - q.y * cq.y, q.y * cq.x + q.x * cq.y);
+    float s[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      s[j] = 0.f;
+      if (j < nk) {
+        const int kp = ks + j;
+        const float* kr = kp < W ? kcn + (size_t)kp * D : kblk + (size_t)(kp - W) * (3 * D);
+        float2 k = *reinterpret_cast<const float2*>(kr + hd * 64 + 2 * lane);
+        if (rot) {
+          const float2 cs = rope_tab[kp * 16 + lane];
+          k = make_float2(k.x * cs.x - k.y * cs.y, k.y * cs.x + k.x * cs.y);
+        }
+        s[j] = fmaf(q.x, k.x, q.y * k.y);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) s[j] = warp_sum(s[j]) * scale;
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) if (j < nk) m = fmaxf(m, s[j]);
+    float l = 0.f;
+    float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      if (j < nk) {
+        const float pr = expf(s[j] - m);
+        l += pr;
+        const int kp = ks + j;
+        const float* vr = kp < W ? vcn + (size_t)kp * D : kblk + D + (size_t)(kp - W) * (3 * D);
+        const float2 v = *reinterpret_cast<const float2*>(vr + hd * 64 + 2 * lane);
+        o.x = fmaf(pr, v.x, o.x);
+        o.y = fmaf(pr, v.y, o.y);
+      }
+    }
+    const float inv = 1.0f / l;
+    const float2 r = *reinterpret_cast<const float2*>(h + (size_t)row * D + hd * 64 + 2 * lane);
+    x[2 * hd] = r.x + o.x * inv;
+    x[2 * hd + 1] = r.y + o.y * inv;
+  }
+  float mean, rstd;
+  row_stats<NH * 2>(x, D, mean, rstd);
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    const int e = hd * 64 + 2 * lane;
+    const float2 al = *reinterpret_cast<const float2*>(ap + e);
+    const float2 be = *reinterpret_cast<const float2*>(ap + D + e);
+    x[2 * hd] = (x[2 * hd] - mean) * rstd * (1.f + al.x) + be.x;
+    x[2 * hd + 1] = (x[2 * hd + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    *reinterpret_cast<float2*>(h + (size_t)row * D + e) = make_float2(x[2 * hd], x[2 * hd + 1]);
+  }
+  row_stats<NH * 2>(x, D, mean, rstd);
+#pragma unroll
+  for (int hd = 0; hd < NH; ++hd) {
+    const int e = hd * 64 + 2 * lane;
+    const float2 g = *reinterpret_cast<const float2*>(g3 + e);
+    const float2 b = *reinterpret_cast<const float2*>(b3 + e);
+    const float ox = (x[2 * hd] - mean) * rstd * g.x + b.x;
+    const float oy = (x[2 * hd + 1] - mean) * rstd * g.y + b.y;
+    const size_t off = (size_t)row * D + e;
+    if (a_out.f32) *reinterpret_cast<float2*>(a_out.f32 + off) = make_float2(ox, oy);
+    if (a_out.hi) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(ox, h0, l0); split_bf16(oy, h1, l1);
+      *reinterpret_cast<uint32_t*>(a_out.hi + off) = pack_bf16x2(h0, h1);
+      if (a_out.lo) *reinterpret_cast<uint32_t*>(a_out.lo + off) = pack_bf16x2(l0, l1);
+    }
+  }
+}
+
+// DenoiserV2.roll_cache (transformerv2.py:167-186): new history = (history ++ first r frames of the last block)[-W:].
+// grid (layer, sequence, {k, v}); one thread per feature column walks the W slots in ascending order, so slot j + r is
+// always read before it is overwritten (r >= 1) and columns never interact.
+__global__ void __launch_bounds__(256)
+kv_roll_kernel(float* kc, float* vc, const float* __restrict__ qkv_stream, int maxN, int maxRows, int T, int W, int r, int D) {
+  pdl_wait();
+  pdl_trigger();
+  const int l = blockIdx.x, n = blockIdx.y, which = blockIdx.z;
+  float* c = (which ? vc : kc) + ((size_t)l * maxN + n) * W * D;
+  const float* last = qkv_stream + ((size_t)l * maxRows + (size_t)n * T) * (3 * D) + (which ? 2 * D : D);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int j = 0; j < W; ++j) {
+      const int src = j + r;
+      c[(size_t)j * D + d] = src < W ? c[(size_t)src * D + d] : last[(size_t)(src - W) * (3 * D) + d];
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // patchify_and_embed: h0[(b,t), :] = GELU(W_in x[b, :, t] + b_in)          (transformerv2.py:387-391, 440)
 // x channel-first (B, C, T); Wt = W_in^T stored [C][D].  Block: 32 frames of one stream, 256 threads.
 // -------------------------------------------------------------------------------------------
@@ -334,6 +483,8 @@ __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
                    float* __restrict__ h0, int C, int T, int D) {
   extern __shared__ float xs[];  // [C][TPB_FRAMES]
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, t0 = blockIdx.x * TPB_FRAMES;
   for (int i = threadIdx.x; i < C * TPB_FRAMES; i += blockDim.x) {
     int c = i / TPB_FRAMES, tt = i % TPB_FRAMES;
@@ -418,6 +569,8 @@ __global__ void __launch_bounds__(256)
 cfg_combine_kernel(const float* __restrict__ proj, const float* __restrict__ guidance, const float* __restrict__ x_in,
                    float* __restrict__ x_out, int B, int C, int T, int euler) {
   __shared__ float tile[32][33];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
   const float g = guidance[0], f = guidance[1], dt = guidance[2];

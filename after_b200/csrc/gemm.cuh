@@ -563,6 +563,8 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail (common.cuh)
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -772,6 +774,8 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail (common.cuh)
+  pdl_trigger();
   if (threadIdx.x == 0) ts_mark(epi, 1);
 
   if (warp == 0) {
@@ -912,9 +916,20 @@ struct LinearProblem {
   int Cin;        // K
   int n_tiles_n;  // N / BN
   int n_tiles;    // n_tiles_n * (#row blocks)
+  // K-split of the down projection (problem 1 only): with ksplit == 2 every output tile is two work items, K halves
+  // [0, K/2) and [K/2, K).  The first half's epilogue is `epi` (bias + residual -> h), the second half's is `epi2`
+  // (plain -> a partial buffer); the consumer of h adds the partial, always in that order, so results stay
+  // deterministic.  Why: 48 down tiles of 24 K-blocks each leave 26 of the 74 clusters idle and put a 20 us mainloop
+  // behind the up-projection's last epilogue; 96 half items spread over all clusters and halve that tail.
+  int ksplit;
+  GemmEpi epi2;
 };
 
-__device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters, int n0, int n1, int& prob, int& tile) {
+// Work list of cluster `cluster_id`: its up-projection tiles (prob 0) first, then down-projection items (prob 1 =
+// first / only K part, prob 2 = second K half); item j of problem 1 is output tile j / ksplit, so both halves of a
+// tile, and the tiles of the row blocks that complete first, come first.
+__device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters, int n0, int n1, int ksplit, int& prob,
+                                           int& tile) {
   const int mine0 = cluster_id < n0 ? (n0 - cluster_id + n_clusters - 1) / n_clusters : 0;
   if (i < mine0) {
     prob = 0;
@@ -922,9 +937,9 @@ __device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters
     return true;
   }
   const int j = (n_clusters - 1 - cluster_id) + (i - mine0) * n_clusters;  // lightest clusters take problem 1 first
-  if (j < n1) {
-    prob = 1;
-    tile = j;
+  if (j < n1 * ksplit) {
+    prob = 1 + (j % ksplit);
+    tile = j / ksplit;
     return true;
   }
   return false;
@@ -985,18 +1000,20 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail (common.cuh)
+  pdl_trigger();
   if (threadIdx.x == 0) mark(0);
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0, prob, tile;
-      for (int i = 0; fused_item(i, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++i) {
+      for (int i = 0; fused_item(i, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++i) {
         const LinearProblem& p = prob ? p1 : p0;
         const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
         const int b = mt / m_tiles_per_b;
         const int t0 = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM;
         const int nrow = nt * BN + (int)rank * (BN / 2);
-        if (prob == 1) {  // the hidden activations of row block mt must be complete and visible to the async proxy
+        if (prob >= 1) {  // the hidden activations of row block mt must be complete and visible to the async proxy
           mark(1);
           int seen;
           long long t_start = clock64();
@@ -1010,8 +1027,9 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
           asm volatile("fence.proxy.async;" ::: "memory");
           mark(2);
         }
-        const int cblocks = p.Cin / BK;
-        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+        const int cblocks = prob ? p.Cin / BK / p1.ksplit : p.Cin / BK;
+        const int cb0 = prob == 2 ? cblocks : 0;
+        for (int cb = cb0; cb < cb0 + cblocks; ++cb, ++it) {
           const int s = it % n_stages;
           const uint32_t par = (it / n_stages) & 1;
           mbar_wait(&empty[s], par ^ 1);
@@ -1032,8 +1050,8 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc2(BN);
       int it = 0, prob, tile;
-      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++ti) {
-        const int nkb = (prob ? p1.Cin : p0.Cin) / BK;
+      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++ti) {
+        const int nkb = prob ? p1.Cin / BK / p1.ksplit : p0.Cin / BK;
         const int buf = ti & 1;
         mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1064,8 +1082,9 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
     const int quad = warp & 3;
     const uint32_t te0 = mapa(smem_u32(&tmem_empty[0]), 0), te1 = mapa(smem_u32(&tmem_empty[1]), 0);
     int prob, tile;
-    for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, prob, tile); ++ti) {
+    for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++ti) {
       const LinearProblem& p = prob ? p1 : p0;
+      const GemmEpi& pe1 = prob == 2 ? p1.epi2 : p1.epi;
       const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
       const int b = mt / m_tiles_per_b;
       const int t_base = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM + quad * 32;
@@ -1087,15 +1106,15 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
           if (prob == 0) {
             if (p0.epi.bias) bias4 = *reinterpret_cast<const float4*>(p0.epi.bias + n0 + c + (lane & 3) * 4);
           } else {
-            epi_prefetch<EPI_PLAIN>(p1.epi, aux, b, t_base, T, n0 + c, lane);
-            if (p1.epi.bias) bias4 = *reinterpret_cast<const float4*>(p1.epi.bias + n0 + c + (lane & 3) * 4);
+            epi_prefetch<EPI_PLAIN>(pe1, aux, b, t_base, T, n0 + c, lane);
+            if (pe1.bias) bias4 = *reinterpret_cast<const float4*>(pe1.bias + n0 + c + (lane & 3) * 4);
           }
           uint32_t v[16];
           tmem_ld16_issue(taddr + c, v);
           tmem_ld_wait();
           if (tr && c == cbeg) mark(9 + 4 * ti);
           if (prob == 0) epi_block<EPI_GELU>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
-          else epi_block<EPI_PLAIN>(p1.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          else epi_block<EPI_PLAIN>(pe1, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
           if (tr && c == cbeg) mark(10 + 4 * ti);
         }
       }

@@ -177,8 +177,8 @@ inline void launch_tap_gemm_tc_bn(const ActOperand::Maps& am, const GemmWeight& 
     attr_set = true;
   }
   dim3 grid(W.N / BN, ceil_div(T, tc::BM), B);
-  tc::tap_gemm_tc_kernel<BN><<<grid, tc::NUM_THREADS, smem, st>>>(am.hi, am.lo, W.map_hi, W.map_lo, epi, W.taps, T, W.Cin, nprod);
-  AFTER_CUDA_CHECK(cudaGetLastError());
+  launch_k(tc::tap_gemm_tc_kernel<BN>, grid, dim3(tc::NUM_THREADS), (size_t)smem, st, am.hi, am.lo, W.map_hi, W.map_lo, epi, W.taps, T,
+           W.Cin, nprod);
 }
 
 template <int BN, int MODE>
@@ -200,9 +200,8 @@ inline void launch_tap_gemm_tc2_bn(const ActOperand::Maps& am, const GemmWeight&
   const int m_tiles_per_b = ceil_div(T, 2 * tc::BM);
   const int n_tiles = n_tiles_n * m_tiles_per_b * B;
   const int clusters = std::min(n_tiles, n_pairs);
-  tc::tap_gemm_tc2_kernel<BN, MODE><<<2 * clusters, tc::NUM_THREADS2, smem, st>>>(am.hi, am.lo, W.map2_hi, W.map2_lo, epi, W.taps, T,
-                                                                            W.Cin, nprod, n_tiles_n, m_tiles_per_b, n_tiles);
-  AFTER_CUDA_CHECK(cudaGetLastError());
+  launch_k(tc::tap_gemm_tc2_kernel<BN, MODE>, dim3(2 * clusters), dim3(tc::NUM_THREADS2), (size_t)smem, st, am.hi, am.lo, W.map2_hi,
+           W.map2_lo, epi, W.taps, T, W.Cin, nprod, n_tiles_n, m_tiles_per_b, n_tiles);
 }
 
 // cudaFuncSetAttribute must not first run inside a stream capture: touch every instantiation once up front.
@@ -237,9 +236,24 @@ inline bool use_fused_mlp() {
   }
   return v == 1;
 }
+// The down projection's K range is split in two work items per tile (see LinearProblem::ksplit); AFTER_MLP_KSPLIT=1
+// turns that off (+3.7 % steps/s at base B=8 with it, profiles/r01b_ab_knobs.jsonl).
+inline int mlp_ksplit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AFTER_MLP_KSPLIT");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+// `partial`: when non-null and the K-split is on, receives the second K half of the down projection ([B*T, ldo] fp32,
+// no bias / residual); the caller adds it to epi1.out_f32 when it next reads that tensor.  *used_partial says whether
+// it was written.
 inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi0, ActOperand& hid, const GemmWeight& W2,
-                             GemmEpi epi1, int B, int T, int precision, int* flags, cudaStream_t st) {
+                             GemmEpi epi1, int B, int T, int precision, int* flags, cudaStream_t st,
+                             float* partial = nullptr, bool* used_partial = nullptr) {
   constexpr int BN = 256;
+  if (used_partial) *used_partial = false;
   if (precision == AFTER_PRECISION_FP32_SIMT || !use_pair_kernel() || !use_fused_mlp()) return false;
   if (!W0.tc2_ok || !W2.tc2_ok || W0.bn2 != BN || W2.bn2 != BN || W0.taps.ntaps != 1 || W2.taps.ntaps != 1) return false;
   if (W0.N != W2.Cin || epi0.out_hi != hid.hi || epi0.out_hi == nullptr || epi0.out_f32 != nullptr) return false;
@@ -266,7 +280,16 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   p0.n_tiles_n = W0.N / BN; p0.n_tiles = p0.n_tiles_n * n_m_tiles;
   p1.a_hi = m1.hi; p1.a_lo = m1.lo; p1.b_hi = W2.map2_hi; p1.b_lo = W2.map2_lo; p1.epi = epi1; p1.Cin = W2.Cin;
   p1.n_tiles_n = W2.N / BN; p1.n_tiles = p1.n_tiles_n * n_m_tiles;
-  const int clusters = std::min(std::max(p0.n_tiles, p1.n_tiles), n_pairs);
+  p0.ksplit = 1; p1.ksplit = 1;
+  if (partial && mlp_ksplit() == 2 && !epi1.out_hi && epi1.out_f32 && (W2.Cin / tc::BK) % 2 == 0) {
+    p1.ksplit = 2;
+    p1.epi2 = GemmEpi{};
+    p1.epi2.out_f32 = partial;
+    p1.epi2.ldo = epi1.ldo;
+    p1.epi2.debug_skip = epi1.debug_skip;
+    if (used_partial) *used_partial = true;
+  }
+  const int clusters = std::min(std::max(p0.n_tiles, p1.n_tiles * p1.ksplit), n_pairs);
   const double rows = (double)B * T;
   ProfScope prof(KC_TAP_GEMM_TC, st, 2.0 * rows * ((double)W0.N * W0.K + (double)W2.N * W2.K),
                  rows * (W0.Cin * 4.0 + W0.N * 4.0 * 2 + W2.N * 8.0));
@@ -283,9 +306,8 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
     dbg_now = dbg;
     AFTER_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 128 * 16 * sizeof(unsigned long long), st));
   }
-  tc::mlp_fused_tc2_kernel<BN><<<2 * clusters, tc::NUM_THREADS2, smem, st>>>(p0, p1, T, nprod, m_tiles_per_b, flags,
-                                                                             2 * p0.n_tiles_n, dbg_now);
-  AFTER_CUDA_CHECK(cudaGetLastError());
+  launch_k(tc::mlp_fused_tc2_kernel<BN>, dim3(2 * clusters), dim3(tc::NUM_THREADS2), (size_t)smem, st, p0, p1, T, nprod,
+           m_tiles_per_b, flags, 2 * p0.n_tiles_n, dbg_now);
   AFTER_COUNT_LAUNCH();
   if (dbg_now) {
     AFTER_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -12,7 +12,11 @@ from .engine import Engine
 
 
 class DenoiserV2:
-    """``net(x, time=, cond=, time_cond=, cache_index=0)`` -- transformerv2.py:514-543 (offline path)."""
+    """``net(x, time=, cond=, time_cond=, cache_index=0)`` + ``roll_cache`` -- transformerv2.py:514-543.
+
+    Like the reference module, which path runs is a construction-time property: an engine created with
+    ``max_cache_size == 0`` is the offline model (``cache_index`` is accepted and, as in the reference, irrelevant); with
+    ``max_cache_size > 0`` every forward attends to -- and ``roll_cache`` extends -- the KV history of ``cache_index``."""
 
     def __init__(self, engine: Engine):
         if not engine.has_denoiser:
@@ -23,13 +27,17 @@ class DenoiserV2:
         return self.forward(x, time=time, cond=cond, time_cond=time_cond, cache_index=cache_index)
 
     def forward(self, x, time, cond, time_cond, cache_index: int = 0):
-        if cache_index != 0:
-            raise NotImplementedError("streaming KV-cache path (cache_index > 0) is not part of the offline hot path")
-        return self.engine.denoiser_forward(x, time, cond, time_cond)
+        return self.engine.denoiser_forward(x, time, cond, time_cond, cache_index if self.engine.streaming else None)
 
     def roll_cache(self, size: int, cache_index: int = 0):
-        """Offline path keeps no cache (max_cache_size = 0 in the reference): nothing to roll."""
-        return None
+        """transformerv2.py:514-515.  The offline model keeps no cache (the reference's ``max_cache_size = 0`` modules
+        would fail here; exported offline models never call it): nothing to roll."""
+        if self.engine.streaming:
+            self.engine.roll_cache(size, cache_index)
+
+    def reset_cache(self):
+        if self.engine.streaming:
+            self.engine.reset_cache()
 
     def eval(self):
         return self
@@ -109,10 +117,9 @@ class RectifiedFlow:
 
     def model_forward(self, x, time, cond, time_cond, guidance_timbre: float, guidance_structure: float,
                       cache_index: int = 0):
-        if cache_index != 0:
-            raise NotImplementedError("streaming KV-cache path is not part of the offline hot path")
-        return self.net.engine.model_forward(x, time, cond, time_cond, guidance_timbre, guidance_structure,
-                                             self.cfg_variant, self.clamp)
+        eng = self.net.engine
+        return eng.model_forward(x, time, cond, time_cond, guidance_timbre, guidance_structure, self.cfg_variant, self.clamp,
+                                 cache_index if eng.streaming else None)
 
     @torch.no_grad()
     def sample(self, x0, cond, time_cond, nb_steps: int, guidance_timbre: float = 1.0, guidance_structure: float = 1.0):

@@ -15,9 +15,11 @@ from .config import AutoEncoderConfig, DenoiserConfig, EcapaConfig, Encoder1DCon
 
 
 def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], max_batch: int, max_steps: int,
-                 seq_len: Optional[int], max_samples: int, use_structure: bool, use_timbre: bool = False) -> L.AfterConfig:
+                 seq_len: Optional[int], max_samples: int, use_structure: bool, use_timbre: bool = False,
+                 max_cache_size: int = 0) -> L.AfterConfig:
     c = L.AfterConfig()
     c.abi_version = L.ABI_VERSION
+    c.max_cache_size = max_cache_size
     d: DenoiserConfig = model.denoiser if model is not None else DenoiserConfig()
     c.n_channels = d.n_channels
     c.seq_len = seq_len if seq_len is not None else d.seq_len
@@ -99,7 +101,10 @@ class Engine:
                  max_batch: int = 8,
                  max_steps: int = 50,
                  seq_len: Optional[int] = None,
-                 max_samples: int = 524288):
+                 max_samples: int = 524288,
+                 max_cache_size: int = 0):
+        """``max_cache_size`` > 0 enables the streaming denoiser (what ``after_scripts/export.py:74-79`` binds to
+        LOCAL_ATTENTION_SIZE): one rolling KV history per ``cache_index`` in [0, max_steps)."""
         self._lib = L.load()
         self._h = C.c_void_p()
         if precision not in L.PRECISIONS:
@@ -109,7 +114,8 @@ class Engine:
         self.model_cfg = model
         self.ae_cfg = autoencoder
         self.cfg = _fill_config(model, autoencoder if autoencoder_state is not None else None, max_batch, max_steps,
-                                seq_len, max_samples, structure_state is not None, timbre_state is not None)
+                                seq_len, max_samples, structure_state is not None, timbre_state is not None,
+                                max_cache_size)
         L.check(self._lib.after_create(C.byref(self.cfg), device, C.byref(self._h)), None, "after_create")
         try:
             if denoiser_state is not None:
@@ -185,7 +191,8 @@ class Engine:
         return int(self._lib.after_ae_ratio(self._h))
 
     # ------------------------------------------------------------------ compute entry points
-    def denoiser_forward(self, x, time, cond, time_cond):
+    def denoiser_forward(self, x, time, cond, time_cond, cache_index: Optional[int] = None):
+        """``cache_index`` None: offline forward; an int: streaming forward against that KV history."""
         x = self._dev(x, "x")
         N, _, T = x.shape
         time = self._dev(time, "time")
@@ -197,9 +204,45 @@ class Engine:
         self._check_cond(cond, time_cond, N, T)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
+            if cache_index is None:
+                L.check(
+                    self._lib.after_denoiser_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(),
+                                                     time_cond.data_ptr(), out.data_ptr(), N, T, self._stream()), self._h,
+                    "after_denoiser_forward")
+            else:
+                L.check(
+                    self._lib.after_denoiser_forward_cached(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(),
+                                                            time_cond.data_ptr(), out.data_ptr(), N, T, int(cache_index),
+                                                            self._stream()), self._h, "after_denoiser_forward_cached")
+        return out
+
+    @property
+    def streaming(self) -> bool:
+        return self.cfg.max_cache_size > 0
+
+    def roll_cache(self, size: int, cache_index: int = 0):
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_roll_cache(self._h, int(size), int(cache_index), self._stream()), self._h,
+                    "after_roll_cache")
+
+    def reset_cache(self):
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_reset_cache(self._h, self._stream()), self._h, "after_reset_cache")
+
+    def sample_stream(self, x_last, cond, time_cond, nb_steps, guidance_timbre=1.0, guidance_structure=1.0,
+                      cfg_variant=L.CFG_AUDIO, clamp=0.1):
+        """One audio block of the exported ``Streamer.sample`` (export.py:398-416): Euler step i uses and rolls KV cache i."""
+        x_last = self._dev(x_last, "x_last")
+        B, _, T = x_last.shape
+        cond = self._dev(cond, "cond")
+        time_cond = self._dev(time_cond, "time_cond")
+        self._check_cond(cond, time_cond, B, T)
+        out = torch.empty_like(x_last)
+        with torch.cuda.device(self.device):
             L.check(
-                self._lib.after_denoiser_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
-                                                 out.data_ptr(), N, T, self._stream()), self._h, "after_denoiser_forward")
+                self._lib.after_sample_stream(self._h, x_last.data_ptr(), cond.data_ptr(), time_cond.data_ptr(), out.data_ptr(),
+                                              B, T, int(nb_steps), float(guidance_timbre), float(guidance_structure),
+                                              int(cfg_variant), float(clamp), self._stream()), self._h, "after_sample_stream")
         return out
 
     def _check_cond(self, cond, time_cond, B, T):
@@ -209,7 +252,7 @@ class Engine:
             raise ValueError(f"time_cond must be ({B}, {self.cfg.tcond_dim}, {T}), got {tuple(time_cond.shape)}")
 
     def model_forward(self, x, time, cond, time_cond, guidance_timbre, guidance_structure, cfg_variant=L.CFG_AUDIO,
-                      clamp=0.01):
+                      clamp=0.01, cache_index: Optional[int] = None):
         x = self._dev(x, "x")
         B, _, T = x.shape
         time = self._dev(time, "time").reshape(B, -1)[:, 0].contiguous()
@@ -218,10 +261,19 @@ class Engine:
         self._check_cond(cond, time_cond, B, T)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            L.check(
-                self._lib.after_model_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
-                                              out.data_ptr(), B, T, float(guidance_timbre), float(guidance_structure),
-                                              int(cfg_variant), float(clamp), self._stream()), self._h, "after_model_forward")
+            if cache_index is None:
+                L.check(
+                    self._lib.after_model_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
+                                                  out.data_ptr(), B, T, float(guidance_timbre), float(guidance_structure),
+                                                  int(cfg_variant), float(clamp), self._stream()), self._h,
+                    "after_model_forward")
+            else:
+                L.check(
+                    self._lib.after_model_forward_cached(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(),
+                                                         time_cond.data_ptr(), out.data_ptr(), B, T, float(guidance_timbre),
+                                                         float(guidance_structure), int(cfg_variant), float(clamp),
+                                                         int(cache_index), self._stream()), self._h,
+                    "after_model_forward_cached")
         return out
 
     def sample(self, x0, cond, time_cond, nb_steps, guidance_timbre=1.0, guidance_structure=1.0, cfg_variant=L.CFG_AUDIO,

@@ -2,10 +2,11 @@
 ``Engine``.  Same method names, channel counts, ratios and attribute setters, so host code written against the exported
 model (notebooks/audio_to_audio_demo.ipynb cell 9, ``nn~ <model> generate_timbre 8192``) runs against it.
 
-Semantics: *block-offline*.  Every call processes its buffer with the offline (cache-free) kernels, i.e. what the
-reference computes with ``cc.use_cached_conv(False)`` and ``max_cache_size = 0``; the cross-buffer state the reference
-keeps in cached convolutions / per-step KV caches is not carried over.  The one piece
-of cross-call state that IS part of the method contract -- the rolling ``previous_timbre`` latent buffer -- is kept.
+Semantics.  Codec and conditioning encoders are *block-offline*: every call processes its buffer with the offline
+kernels, i.e. what the reference computes with ``cc.use_cached_conv(False)``; the cross-buffer state the reference keeps in
+cached convolutions is not carried over.  The denoiser IS streamed when the engine was created with ``max_cache_size > 0``
+(``export.py:74-79`` binds it to LOCAL_ATTENTION_SIZE): one rolling KV history per diffusion step, exactly as in
+``export.py:398-416``.  The rolling ``previous_timbre`` latent buffer, part of the method contract, is kept.
 TorchScript serialisation (``export_to_ts``) and the latent-map MLP (``latent2map`` / ``map2latent``) are out of scope.
 """
 from __future__ import annotations
@@ -82,7 +83,12 @@ class Streamer:
         return x.to(self.engine.device, torch.float32).contiguous()
 
     def sample(self, x_last, cond, time_cond):
-        """export.py:398-416 without the per-step KV caches; the streamer clamps the guidance ratio at 0.1 (:389-390)."""
+        """export.py:398-416; the streamer clamps the guidance ratio at 0.1 (:389-390).  On an engine created with
+        ``max_cache_size > 0`` Euler step i attends to, and then rolls, KV history i (the exported model's behaviour);
+        otherwise the block is sampled with the offline kernels."""
+        if self.engine.streaming:
+            return self.engine.sample_stream(x_last, cond, time_cond, self.nb_steps[0], self.guidance_timbre[0],
+                                             self.guidance_structure[0], cfg_variant=L.CFG_AUDIO, clamp=0.1)
         return self.engine.sample(x_last, cond, time_cond, self.nb_steps[0], self.guidance_timbre[0],
                                   self.guidance_structure[0], cfg_variant=L.CFG_AUDIO, clamp=0.1)
 

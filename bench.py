@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--nb-steps", type=int, default=50, help="diffusion (Euler) steps per sample call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chain", action="store_true", help="skip the full-chain RTF leg")
+    ap.add_argument("--no-stream", action="store_true", help="skip the streaming-block latency leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -281,6 +282,32 @@ def main():
                    "e2e_h2d_bytes_per_step": int(4 * (2 * a_s_h.numel() + x0_h.numel())), "e2e_d2h_bytes_per_step": int(4 * audio_out_h.numel()),
                    "chain": "after_generate: 2x AutoEncoder.encode + Encoder1D + ECAPATDNN + sample(50 steps, CFG) + AutoEncoder.decode"}
 
+    # ---- streaming (live nn~ use): latency of one 4-frame block (8192 samples = 185.8 ms of audio) through the
+    # per-diffusion-step KV caches, B = 1 stream (3 CFG rows), as the exported Streamer.sample runs it -----------------
+    stream = None
+    if rank == 0 and not args.no_stream:
+        s_steps, s_frames = 8, 4
+        s_eng = Engine(model=mc, denoiser_state=den_sd, precision=args.precision, device=local, max_batch=1, max_steps=s_steps,
+                       seq_len=s_frames, max_cache_size=mc.denoiser.local_attention_size)
+        sx, sc, st_ = x0[:1, :, :s_frames].contiguous(), cond[:1].contiguous(), tc[:1, :, :s_frames].contiguous()
+        for _ in range(5):
+            s_eng.sample_stream(sx, sc, st_, s_steps, 2.0, 1.0)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+        for a, b in evs:
+            a.record()
+            s_eng.sample_stream(sx, sc, st_, s_steps, 2.0, 1.0)
+            b.record()
+        torch.cuda.synchronize()
+        per_blk = sorted(a.elapsed_time(b) for a, b in evs)
+        blk_audio_ms = s_frames * 2048 / SR * 1e3
+        stream = {"block_frames": s_frames, "block_audio_ms": blk_audio_ms, "nb_steps": s_steps, "cache_frames": mc.denoiser.local_attention_size,
+                  "median_ms_per_block": per_blk[len(per_blk) // 2], "p95_ms_per_block": per_blk[int(len(per_blk) * 0.95)],
+                  "diffusion_steps_per_s": s_steps / (per_blk[len(per_blk) // 2] / 1e3),
+                  "realtime_margin": blk_audio_ms / per_blk[len(per_blk) // 2],
+                  "what": "after_sample_stream: one CUDA-graph replay per block (sampler only; codec not included)"}
+        s_eng.close()
+
     # ---- roofline of the dominant kernel (tcgen05 tap-GEMM), per-launch CUDA events on the launching stream ----------
     pk = peaks()
     roof = None
@@ -325,7 +352,7 @@ def main():
             "config": workload_config(args, world),
             "sequence_steps_per_s": value * B,
             "algorithmic_tflops": 3 * B * FLOP_PER_SEQ[args.model] * NS * args.steps * world / (total_ms / 1e3) / 1e12,
-            "e2e": e2e, "rtf": rtf, "roofline": roof, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
+            "e2e": e2e, "rtf": rtf, "stream": stream, "roofline": roof, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
             "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in (prof or {}).items()},
         }
         print(json.dumps(line))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AFTER_B200_ABI_VERSION 1
+#define AFTER_B200_ABI_VERSION 2
 
 /* error codes */
 #define AFTER_OK 0
@@ -117,6 +117,9 @@ typedef struct after_config {
   int32_t te_out_dim;                        /* zt = 6 */
   int32_t te_global_context;                 /* 1 */
   int32_t te_use_tanh;
+  /* --- streaming (transformerv2.py:119-155; after_scripts/export.py:74-79 binds it to LOCAL_ATTENTION_SIZE) --- */
+  int32_t max_cache_size; /* frames of key/value history per (layer, diffusion step, sequence); 0 = offline only.
+                             One history per cache_index in [0, max_steps) and per sequence in [0, 3*max_batch). */
 } after_config;
 
 typedef struct after_ctx* after_handle;
@@ -165,6 +168,28 @@ int after_sample(after_handle h, const float* x0, const float* cond, const float
 int after_sample_host(after_handle h, const float* x0, const float* cond, const float* time_cond,
                       float* out, int B, int T, int nb_steps, float guidance_timbre,
                       float guidance_structure, int cfg_variant, float clamp, void* stream);
+
+/* ---- streaming denoiser: per-diffusion-step rolling key/value caches (needs after_config.max_cache_size > 0) ----
+ * after_denoiser_forward_cached: DenoiserV2.forward(..., cache_index) with MHAttention.max_cache_size > 0
+ *   (transformerv2.py:190-236, 517-543): the block's keys/values are appended to the history of `cache_index`
+ *   for attention (history cached un-rotated, queries rotated at offset = history length), and remembered as
+ *   last_k / last_v.  The history starts as zeros, exactly like the reference's registered buffers.
+ * after_model_forward_cached: RectifiedFlow.model_forward(..., cache_index) (model.py:721-761; exported
+ *   Streamer.model_forward, after_scripts/export.py:356-396).
+ * after_roll_cache: DenoiserV2.roll_cache(size, cache_index) (transformerv2.py:167-186, 433-435, 514-515).
+ * after_reset_cache: zero every history (what re-instantiating the reference module does).
+ * after_sample_stream: one audio block of the exported Streamer.sample (export.py:398-416): for step i,
+ *   x += model_forward(x, t_i, ..., cache_index=i) / nb_steps, then roll_cache(T, i).  x_last,out dev (B,C,T). */
+int after_denoiser_forward_cached(after_handle h, const float* x, const float* time, const float* cond,
+                                  const float* time_cond, float* out, int N, int T, int cache_index, void* stream);
+int after_model_forward_cached(after_handle h, const float* x, const float* time, const float* cond,
+                               const float* time_cond, float* out, int B, int T, float guidance_timbre,
+                               float guidance_structure, int cfg_variant, float clamp, int cache_index, void* stream);
+int after_roll_cache(after_handle h, int roll_size, int cache_index, void* stream);
+int after_reset_cache(after_handle h, void* stream);
+int after_sample_stream(after_handle h, const float* x_last, const float* cond, const float* time_cond, float* out,
+                        int B, int T, int nb_steps, float guidance_timbre, float guidance_structure, int cfg_variant,
+                        float clamp, void* stream);
 
 /* AutoEncoder.encode (SimpleNetsStream.py:918-941; z only, as export_autoencoder.py:251-258):
  * audio dev (B,1,S) -> z dev (B,Z,S/ratio).  S must be a multiple of the codec ratio. */

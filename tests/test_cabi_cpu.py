@@ -33,7 +33,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_build_info(lib):
-    assert lib.after_abi_version() == 1
+    from after_b200 import _lib
+    assert lib.after_abi_version() == _lib.ABI_VERSION == 2
     assert b"sm_100a" in lib.after_build_info()
 
 
@@ -42,7 +43,8 @@ def test_config_struct_layout_matches_header(lib, tmp_path):
     import subprocess
     from after_b200 import _lib
     src = tmp_path / "sz.c"
-    fields = ["abi_version", "drop_value", "max_steps", "ae_multipliers", "ae_max_samples", "se_in_size", "se_use_tanh"]
+    fields = ["abi_version", "drop_value", "max_steps", "ae_multipliers", "ae_max_samples", "se_in_size", "se_use_tanh",
+              "max_cache_size"]
     body = "".join(f'printf("%zu\\n", offsetof(after_config, {f}));' for f in fields)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "after_b200.h"\n'
                    f'int main(void){{printf("%zu\\n", sizeof(after_config));{body}return 0;}}\n')
@@ -58,7 +60,7 @@ def test_config_struct_layout_matches_header(lib, tmp_path):
 def test_no_gpu_means_loud_failure(lib):
     from after_b200 import _lib
     cfg = _lib.AfterConfig()
-    cfg.abi_version = 1
+    cfg.abi_version = _lib.ABI_VERSION
     h = C.c_void_p()
     rc = lib.after_create(C.byref(cfg), 0, C.byref(h))
     assert rc < 0
