@@ -12,6 +12,7 @@
 // (B, T, steps, variant) signature and replayed.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <tuple>
 #include "context.cuh"
 #include "denoiser_kernels.cuh"
@@ -179,6 +180,18 @@ struct Denoiser {
     guidance = arena->alloc<float>(4);
     flag_stride = maxN * ceil_div(maxT, 2 * tc::BM);
     mlp_flags = arena->alloc<int>((size_t)L * flag_stride);
+    {  // opt-in dynamic shared memory of the bulk-copy attention kernel (must not first happen inside a stream capture)
+      auto set = [](const void* f, size_t bytes) {
+        AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      };
+      auto bytes = [](int nh, int maxk) { return 128 + (size_t)(4 + 2 * maxk) * nh * 64 * sizeof(float); };
+      set((const void*)attn_chunk4_bulk_kernel<8, 12>, bytes(8, 12));
+      set((const void*)attn_chunk4_bulk_kernel<8, 20>, bytes(8, 20));
+      set((const void*)attn_chunk4_bulk_kernel<8, 32>, bytes(8, 32));
+      set((const void*)attn_chunk4_bulk_kernel<4, 12>, bytes(4, 12));
+      set((const void*)attn_chunk4_bulk_kernel<4, 20>, bytes(4, 20));
+      set((const void*)attn_chunk4_bulk_kernel<4, 32>, bytes(4, 32));
+    }
     cacheW = c.max_cache_size;
     AFTER_REQUIRE(cacheW >= 0 && cacheW <= 64, AFTER_EINVAL, "max_cache_size must be in [0, 64]");
     if (cacheW > 0) {
@@ -260,7 +273,24 @@ struct Denoiser {
     // q,k,v read once + h read/write + operand write; ~2 * keys * 64 * 2 flops per (token, head)
     ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
-    if (cfg.attention_chunk_size == 4) {
+    static int variant = -1;  // AFTER_ATTN = warp (default) | block | bulk  (A/B runs)
+    if (variant < 0) {
+      const char* e = getenv("AFTER_ATTN");
+      variant = (e && !strcmp(e, "block")) ? 1 : (e && !strcmp(e, "bulk")) ? 2 : 0;
+    }
+    if (cfg.attention_chunk_size == 4 && variant == 0 && MAXK <= 20) {  // wider bands: sc[4][MAXK] would spill
+      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
+      launch_k(attn_warp_chunk_kernel<NH, MAXK>, dim3(ceil_div(chunks, 4)), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D,
+               l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
+               mlp_flags + (size_t)l * flag_stride, flag_stride);
+    } else if (cfg.attention_chunk_size == 4 && variant == 2) {
+      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
+      const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
+      const size_t smem = 128 + (size_t)(4 + 2 * mk) * D * sizeof(float);
+      launch_k(attn_chunk4_bulk_kernel<NH, MAXK>, dim3(chunks), dim3(NH * 32), smem, st, qkv, h, o, adaC_step, L * 2 * D,
+               l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
+               mlp_flags + (size_t)l * flag_stride, flag_stride);
+    } else if (cfg.attention_chunk_size == 4) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
       launch_k(attn_chunk4_kernel<NH, MAXK>, dim3(chunks), dim3(NH * 32), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
                seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,

@@ -252,6 +252,343 @@ attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
   }
 }
 
+// Same computation with the key/value rows of the chunk staged in shared memory by bulk async copies: row j of the
+// QKV buffer holds K | V contiguously (2 D floats = 4 KB at D = 512), so one elected thread issues one
+// cp.async.bulk per visible key row against an mbarrier and the whole block waits ONCE, instead of every warp walking
+// ~15 dependent L2 round trips (with <= 64 registers per thread the compiler cannot keep 2 x 11 float4 loads in
+// flight, see the SASS of the kernel above).  The score / softmax / PV loops then read shared memory (8 lanes of a
+// query read 128 contiguous bytes, the 4 query groups broadcast).  Dynamic smem: mk * 2D + 4D floats + one mbarrier.
+template <int NH, int MAXK>
+__global__ void __launch_bounds__(NH * 32, 32 / NH)
+attn_chunk4_bulk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
+                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
+                        const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
+                        int* zero_flags, int n_zero) {
+  constexpr int D = NH * 64;
+  constexpr int NV = D / 32;
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(attn_smem);
+  float* xs = reinterpret_cast<float*>(attn_smem + 128);  // [4][D]
+  float* kv = xs + 4 * D;                                   // [mk][2 D]: K | V of key row ks0 + j
+  const int chunks_per_seq = (T + 3) >> 2;
+  const int n = blockIdx.x / chunks_per_seq;
+  const int c0 = (blockIdx.x - n * chunks_per_seq) * 4;
+  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ce = min(c0 + 4, T);
+  const int ks0 = max(0, c0 - window + 1);
+  const int nk = ce - ks0;  // <= MAXK
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
+  if (threadIdx.x == 0) {
+    const uint32_t row_bytes = 2 * D * sizeof(float);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * nk) : "memory");
+    const float* src = qkv + ((size_t)n * T + ks0) * (3 * D) + D;
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(kv);
+    for (int j = 0; j < nk; ++j) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar_s) : "memory");
+      src += 3 * D;
+      dst += row_bytes;
+    }
+  }
+  {
+    const int qi = lane >> 3, dsub = lane & 7;
+    const int t = min(c0 + qi, T - 1);
+    const int ks = min(c0, max(0, t - window + 1));
+    const int skip = ks - ks0;
+    const size_t row = (size_t)n * T + t;
+    const float* qrow = qkv + row * (3 * D) + hd * 64 + dsub * 4;
+    float4 q0 = *reinterpret_cast<const float4*>(qrow);
+    float4 q1 = *reinterpret_cast<const float4*>(qrow + 32);
+    const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
+    const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
+    const float qs = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64): softmax in the log2 domain
+    const float2 qa = make_float2(q0.x * qs, q0.y * qs), qb = make_float2(q0.z * qs, q0.w * qs);
+    const float2 qc = make_float2(q1.x * qs, q1.y * qs), qd = make_float2(q1.z * qs, q1.w * qs);
+    __syncthreads();  // mbarrier initialised before anyone polls it
+    {
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(bar_s) : "memory");
+      }
+    }
+    const float* kb = kv + hd * 64 + dsub * 4;
+    float sc[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      sc[j] = 0.f;
+      if (j < nk) {
+        const float4 k0 = *reinterpret_cast<const float4*>(kb + j * (2 * D));
+        const float4 k1 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + 32);
+        float2 acc = __fmul2_rn(qa, make_float2(k0.x, k0.y));
+        acc = __ffma2_rn(qb, make_float2(k0.z, k0.w), acc);
+        acc = __ffma2_rn(qc, make_float2(k1.x, k1.y), acc);
+        acc = __ffma2_rn(qd, make_float2(k1.z, k1.w), acc);
+        sc[j] = acc.x + acc.y;
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      float v = sc[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v = (j >= skip && j < nk) ? v : -INFINITY;
+      sc[j] = v;
+      m = fmaxf(m, v);
+    }
+    float l = 0.f;
+    float2 o01 = make_float2(0.f, 0.f), o23 = o01, o45 = o01, o67 = o01;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      if (j < nk) {
+        float p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(sc[j] - m));
+        l += p;
+        const float4 v0 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + D);
+        const float4 v1 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + D + 32);
+        const float2 pp = make_float2(p, p);
+        o01 = __ffma2_rn(pp, make_float2(v0.x, v0.y), o01);
+        o23 = __ffma2_rn(pp, make_float2(v0.z, v0.w), o23);
+        o45 = __ffma2_rn(pp, make_float2(v1.x, v1.y), o45);
+        o67 = __ffma2_rn(pp, make_float2(v1.z, v1.w), o67);
+      }
+    }
+    const float inv = 1.0f / l;
+    float* xp = xs + qi * D + hd * 64 + dsub * 4;
+    *reinterpret_cast<float4*>(xp) = make_float4(fmaf(o01.x, inv, r0.x), fmaf(o01.y, inv, r0.y), fmaf(o23.x, inv, r0.z), fmaf(o23.y, inv, r0.w));
+    *reinterpret_cast<float4*>(xp + 32) = make_float4(fmaf(o45.x, inv, r1.x), fmaf(o45.y, inv, r1.y), fmaf(o67.x, inv, r1.z), fmaf(o67.y, inv, r1.w));
+  }
+  __syncthreads();
+  const int qi = hd;  // phase 2: warp w normalises query row w
+  if (qi >= 4 || c0 + qi >= T) return;
+  const size_t row = (size_t)n * T + c0 + qi;
+  float x[NV];
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + qi * D + (i * 32 + lane) * 4);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  float mean, rstd;
+  row_stats<NV>(x, D, mean, rstd);
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 al = *reinterpret_cast<const float4*>(ap + e);
+    const float4 be = *reinterpret_cast<const float4*>(ap + D + e);
+    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
+    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
+    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
+    *reinterpret_cast<float4*>(h + row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  }
+  row_stats<NV>(x, D, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(g3 + e);
+    const float4 bb = *reinterpret_cast<const float4*>(b3 + e);
+    float4 o;
+    o.x = (x[4 * i + 0] - mean) * rstd * g.x + bb.x;
+    o.y = (x[4 * i + 1] - mean) * rstd * g.y + bb.y;
+    o.z = (x[4 * i + 2] - mean) * rstd * g.z + bb.z;
+    o.w = (x[4 * i + 3] - mean) * rstd * g.w + bb.w;
+    store_operand4(a_out, row * D + e, o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Register-tiled variant: ONE WARP per attention chunk, all heads at once.  Lane = (head hd = lane / LPH, slice
+// dq = lane % LPH) with LPH = 32 / NH lanes per head; the lane owns F = 16 / LPH float4 groups of its head,
+// group i = float4 number dq + LPH * i (so the LPH lanes of a head read LPH consecutive float4 = whole sectors), for
+// ALL FOUR queries of the chunk.  Every key / value float4 is therefore loaded once per chunk and used for four
+// queries (the kernels above load it once per query: 4x the load instructions, and 8 lanes x 3 shuffles per score
+// instead of LPH lanes x log2(LPH)); ncu on the block-per-chunk kernel: 8.6 M warp instructions per launch at 31 %
+// issue utilisation, long-scoreboard bound with 6.4 warps per scheduler -- this layout needs ~2 M.
+// Everything after the PV product (residual, LayerNorm, AdaLN-c, LayerNorm, operand split) stays in registers: a row
+// is spread over the 32 lanes, so each norm is two warp reductions; no shared memory, no block barrier.
+// -------------------------------------------------------------------------------------------
+template <int NH, int MAXK>
+__global__ void __launch_bounds__(128, NH == 8 ? 3 : 4)
+attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
+                       const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
+                       const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
+                       int* zero_flags, int n_zero) {
+  constexpr int D = NH * 64;
+  constexpr int LPH = 32 / NH;   // lanes per head
+  constexpr int F = 16 / LPH;    // float4 groups per lane and row
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
+  const int chunks_per_seq = (T + 3) >> 2;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= n_seq * chunks_per_seq) return;
+  const int lane = threadIdx.x & 31;
+  const int n = chunk / chunks_per_seq;
+  const int c0 = (chunk - n * chunks_per_seq) * 4;
+  const int ce = min(c0 + 4, T);
+  const int ks0 = max(0, c0 - window + 1);
+  const int nk = ce - ks0;  // <= MAXK
+  const int hd = lane / LPH, dq = lane - hd * LPH;
+  const int eoff = hd * 64 + dq * 4;  // element offset of float4 group 0 inside a row; group i adds 4 * LPH * i
+  const size_t row0 = (size_t)n * T + c0;
+
+  // ---- queries (scaled into the log2 domain) -----------------------------------------------------------------
+  float4 q[4][F];
+  const float qs = 0.125f * 1.4426950408889634f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int t = min(c0 + r, T - 1);  // ragged last chunk: surplus rows recompute the last one and are not stored
+    const float* qp = qkv + ((size_t)n * T + t) * (3 * D) + eoff;
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+      float4 v = *reinterpret_cast<const float4*>(qp + 4 * LPH * i);
+      q[r][i] = make_float4(v.x * qs, v.y * qs, v.z * qs, v.w * qs);
+    }
+  }
+  // ---- scores --------------------------------------------------------------------------------------------------
+  const float* kbase = qkv + ((size_t)n * T + ks0) * (3 * D) + D + eoff;
+  float sc[4][MAXK];
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    float2 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
+    if (j < nk) {
+      const float* kp = kbase + (size_t)j * (3 * D);
+#pragma unroll
+      for (int i = 0; i < F; ++i) {
+        const float4 k = *reinterpret_cast<const float4*>(kp + 4 * LPH * i);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          acc[r] = __ffma2_rn(make_float2(q[r][i].x, q[r][i].y), make_float2(k.x, k.y), acc[r]);
+          acc[r] = __ffma2_rn(make_float2(q[r][i].z, q[r][i].w), make_float2(k.z, k.w), acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float v = acc[r].x + acc[r].y;
+#pragma unroll
+      for (int o = 1; o < LPH; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      // key ks0 + j is visible to query c0 + r iff it is not older than the window (all keys of the chunk are visible)
+      const int ks = min(c0, max(0, c0 + r - window + 1));
+      sc[r][j] = (j < nk && ks0 + j >= ks) ? v : -INFINITY;
+    }
+  }
+  // ---- softmax (log2 domain) and P.V ---------------------------------------------------------------------------
+  float m[4], l[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    m[r] = sc[r][0];
+#pragma unroll
+    for (int j = 1; j < MAXK; ++j) m[r] = fmaxf(m[r], sc[r][j]);
+    l[r] = 0.f;
+  }
+  float4 o[4][F];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int i = 0; i < F; ++i) o[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* vbase = kbase + D;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    if (j < nk) {
+      float p[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[r]) : "f"(sc[r][j] - m[r]));  // 2^(-inf) = 0 for masked keys
+        l[r] += p[r];
+      }
+      const float* vp = vbase + (size_t)j * (3 * D);
+#pragma unroll
+      for (int i = 0; i < F; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(vp + 4 * LPH * i);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 pp = make_float2(p[r], p[r]);
+          float2 a = __ffma2_rn(pp, make_float2(v.x, v.y), make_float2(o[r][i].x, o[r][i].y));
+          float2 b = __ffma2_rn(pp, make_float2(v.z, v.w), make_float2(o[r][i].z, o[r][i].w));
+          o[r][i] = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
+    }
+  }
+  // ---- residual, LayerNorm -> AdaLN-c -> h ; LayerNorm(affine) -> operand ------------------------------------------
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off + eoff;
+  float4 al[F], be[F], gg[F], bb[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+    al[i] = *reinterpret_cast<const float4*>(ap + 4 * LPH * i);
+    be[i] = *reinterpret_cast<const float4*>(ap + D + 4 * LPH * i);
+    gg[i] = *reinterpret_cast<const float4*>(g3 + eoff + 4 * LPH * i);
+    bb[i] = *reinterpret_cast<const float4*>(b3 + eoff + 4 * LPH * i);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int t = min(c0 + r, T - 1);
+    const size_t roff = ((size_t)n * T + t) * D + eoff;
+    const float inv = 1.0f / l[r];
+    float x[4 * F];
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+      const float4 res = *reinterpret_cast<const float4*>(h + roff + 4 * LPH * i);
+      x[4 * i + 0] = fmaf(o[r][i].x, inv, res.x);
+      x[4 * i + 1] = fmaf(o[r][i].y, inv, res.y);
+      x[4 * i + 2] = fmaf(o[r][i].z, inv, res.z);
+      x[4 * i + 3] = fmaf(o[r][i].w, inv, res.w);
+      s1 += (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
+    }
+    float mean = warp_sum(s1) / (float)D;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4 * F; ++i) { const float d = x[i] - mean; s2 = fmaf(d, d, s2); }
+    float rstd = 1.0f / sqrtf(warp_sum(s2) / (float)D + 1e-5f);
+    s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+      x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al[i].x) + be[i].x;
+      x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al[i].y) + be[i].y;
+      x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al[i].z) + be[i].z;
+      x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al[i].w) + be[i].w;
+      s1 += (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
+    }
+    const bool store = c0 + r < T;
+    if (store) {
+#pragma unroll
+      for (int i = 0; i < F; ++i)
+        *reinterpret_cast<float4*>(h + roff + 4 * LPH * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    }
+    mean = warp_sum(s1) / (float)D;
+    s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4 * F; ++i) { const float d = x[i] - mean; s2 = fmaf(d, d, s2); }
+    rstd = 1.0f / sqrtf(warp_sum(s2) / (float)D + 1e-5f);
+    if (store) {
+#pragma unroll
+      for (int i = 0; i < F; ++i) {
+        float4 ov;
+        ov.x = (x[4 * i + 0] - mean) * rstd * gg[i].x + bb[i].x;
+        ov.y = (x[4 * i + 1] - mean) * rstd * gg[i].y + bb[i].y;
+        ov.z = (x[4 * i + 2] - mean) * rstd * gg[i].z + bb[i].z;
+        ov.w = (x[4 * i + 3] - mean) * rstd * gg[i].w + bb[i].w;
+        store_operand4(a_out, roff + 4 * LPH * i, ov);
+      }
+    }
+  }
+}
+
 // One warp per token (any chunk size): for head hd the lane owns dims (2*lane, 2*lane+1) of that head.
 template <int NH, int MAXK>
 __global__ void __launch_bounds__(128)
