@@ -191,6 +191,11 @@ struct Denoiser {
       set((const void*)attn_chunk4_bulk_kernel<4, 12>, bytes(4, 12));
       set((const void*)attn_chunk4_bulk_kernel<4, 20>, bytes(4, 20));
       set((const void*)attn_chunk4_bulk_kernel<4, 32>, bytes(4, 32));
+      auto wbytes = [](int nh, int maxk) { return 128 + (size_t)(16 + maxk) * 2 * nh * 64 * sizeof(float); };
+      set((const void*)attn_warp_chunk_kernel<8, 12, true>, wbytes(8, 12));
+      set((const void*)attn_warp_chunk_kernel<8, 20, true>, wbytes(8, 20));
+      set((const void*)attn_warp_chunk_kernel<4, 12, true>, wbytes(4, 12));
+      set((const void*)attn_warp_chunk_kernel<4, 20, true>, wbytes(4, 20));
     }
     cacheW = c.max_cache_size;
     AFTER_REQUIRE(cacheW >= 0 && cacheW <= 64, AFTER_EINVAL, "max_cache_size must be in [0, 64]");
@@ -273,15 +278,24 @@ struct Denoiser {
     // q,k,v read once + h read/write + operand write; ~2 * keys * 64 * 2 flops per (token, head)
     ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
-    static int variant = -1;  // AFTER_ATTN = warp (default) | block | bulk  (A/B runs)
+    // AFTER_ATTN = warp (default) | staged | block | bulk  (A/B runs; measured at base B=8 fp32: 1354 / 1309 / 1314 / 1287
+    // steps/s, profiles/r01b_ab_attn*.jsonl -- staging the key rows in shared memory costs occupancy and a second wave)
+    static int variant = -1;
     if (variant < 0) {
       const char* e = getenv("AFTER_ATTN");
-      variant = (e && !strcmp(e, "block")) ? 1 : (e && !strcmp(e, "bulk")) ? 2 : 0;
+      variant = (e && !strcmp(e, "block")) ? 1 : (e && !strcmp(e, "bulk")) ? 2 : (e && !strcmp(e, "staged")) ? 0 : 3;
     }
-    if (cfg.attention_chunk_size == 4 && variant == 0 && MAXK <= 20) {  // wider bands: sc[4][MAXK] would spill
-      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      launch_k(attn_warp_chunk_kernel<NH, MAXK>, dim3(ceil_div(chunks, 4)), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D,
+    const bool warp_ok = cfg.attention_chunk_size == 4 && MAXK <= 20;  // wider bands: sc[4][MAXK] would spill
+    if (warp_ok && variant == 0 && T % 16 == 0) {
+      const int n_seq = rows / T, chunks = n_seq * (T / 4);
+      const size_t smem = 128 + (size_t)(16 + cfg.local_attention_size - 1) * 2 * D * sizeof(float);
+      launch_k(attn_warp_chunk_kernel<NH, MAXK, true>, dim3(chunks / 4), dim3(128), smem, st, qkv, h, o, adaC_step, L * 2 * D,
                l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
+               mlp_flags + (size_t)l * flag_stride, flag_stride);
+    } else if (warp_ok && (variant == 0 || variant == 3)) {
+      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
+      launch_k(attn_warp_chunk_kernel<NH, MAXK, false>, dim3(ceil_div(chunks, 4)), dim3(128), 0, st, qkv, h, o, adaC_step,
+               L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
                mlp_flags + (size_t)l * flag_stride, flag_stride);
     } else if (cfg.attention_chunk_size == 4 && variant == 2) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);

@@ -418,7 +418,13 @@ attn_chunk4_bulk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
 // Everything after the PV product (residual, LayerNorm, AdaLN-c, LayerNorm, operand split) stays in registers: a row
 // is spread over the 32 lanes, so each norm is two warp reductions; no shared memory, no block barrier.
 // -------------------------------------------------------------------------------------------
-template <int NH, int MAXK>
+// STAGED = true (needs T % 16 == 0 so that the 4 warps of a block are 4 consecutive chunks of one sequence): the
+// <= 16 + window - 1 key rows the block needs (K | V contiguous, 2 D floats each) are brought into shared memory by
+// one cp.async.bulk per row against an mbarrier while the queries are loaded; the score and P.V loops then read
+// shared memory.  With 10 warps per SM (one wave) the direct-load version is bound by exposed L2 latency
+// (ncu: 5.3 long-scoreboard stall cycles per issue at 2.5 warps per scheduler); staging exposes ONE round trip and
+// reads every key row once per 16 queries instead of once per 4.
+template <int NH, int MAXK, bool STAGED>
 __global__ void __launch_bounds__(128, NH == 8 ? 3 : 4)
 attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
@@ -427,11 +433,41 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
   constexpr int D = NH * 64;
   constexpr int LPH = 32 / NH;   // lanes per head
   constexpr int F = 16 / LPH;    // float4 groups per lane and row
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  const int chunks_per_seq = (T + 3) >> 2;
+  uint32_t bar_s = 0;
+  if (STAGED) {
+    bar_s = (uint32_t)__cvta_generic_to_shared(attn_smem);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   pdl_wait();
   pdl_trigger();
   if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
-  const int chunks_per_seq = (T + 3) >> 2;
   const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int srow0 = 0;  // first key row held in shared memory
+  if (STAGED) {
+    const int chunk_b = blockIdx.x * 4;  // the block's chunks lie in one sequence (T % 16 == 0)
+    const int nb = chunk_b / chunks_per_seq;
+    const int c0b = (chunk_b - nb * chunks_per_seq) * 4;
+    srow0 = max(0, c0b - window + 1);
+    if (threadIdx.x == 0) {
+      const int nrows = min(c0b + 16, T) - srow0;
+      const uint32_t row_bytes = 2 * D * sizeof(float);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * nrows) : "memory");
+      const float* src = qkv + ((size_t)nb * T + srow0) * (3 * D) + D;
+      uint32_t dst = bar_s + 128;
+      for (int j = 0; j < nrows; ++j) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar_s) : "memory");
+        src += 3 * D;
+        dst += row_bytes;
+      }
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it (no thread exits before this point)
+  }
   if (chunk >= n_seq * chunks_per_seq) return;
   const int lane = threadIdx.x & 31;
   const int n = chunk / chunks_per_seq;
@@ -441,7 +477,6 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
   const int nk = ce - ks0;  // <= MAXK
   const int hd = lane / LPH, dq = lane - hd * LPH;
   const int eoff = hd * 64 + dq * 4;  // element offset of float4 group 0 inside a row; group i adds 4 * LPH * i
-  const size_t row0 = (size_t)n * T + c0;
 
   // ---- queries (scaled into the log2 domain) -----------------------------------------------------------------
   float4 q[4][F];
@@ -457,7 +492,18 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
     }
   }
   // ---- scores --------------------------------------------------------------------------------------------------
-  const float* kbase = qkv + ((size_t)n * T + ks0) * (3 * D) + D + eoff;
+  // key row ks0 + j: K at kbase + j * kstride, V at + D more (global: rows of the QKV buffer; staged: K | V rows in smem)
+  const float* kbase = STAGED ? reinterpret_cast<const float*>(attn_smem + 128) + (size_t)(ks0 - srow0) * (2 * D) + eoff
+                              : qkv + ((size_t)n * T + ks0) * (3 * D) + D + eoff;
+  constexpr int kstride = STAGED ? 2 * D : 3 * D;
+  if (STAGED) {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok) : "r"(bar_s) : "memory");
+    }
+  }
   float sc[4][MAXK];
 #pragma unroll
   for (int j = 0; j < MAXK; ++j) {
@@ -465,7 +511,7 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
     if (j < nk) {
-      const float* kp = kbase + (size_t)j * (3 * D);
+      const float* kp = kbase + (size_t)j * kstride;
 #pragma unroll
       for (int i = 0; i < F; ++i) {
         const float4 k = *reinterpret_cast<const float4*>(kp + 4 * LPH * i);
@@ -510,7 +556,7 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[r]) : "f"(sc[r][j] - m[r]));  // 2^(-inf) = 0 for masked keys
         l[r] += p[r];
       }
-      const float* vp = vbase + (size_t)j * (3 * D);
+      const float* vp = vbase + (size_t)j * kstride;
 #pragma unroll
       for (int i = 0; i < F; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(vp + 4 * LPH * i);
