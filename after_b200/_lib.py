@@ -18,7 +18,8 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_simt": PRECI
 DTYPE_F32, DTYPE_F64, DTYPE_I64 = 0, 1, 2
 MODULE_DENOISER, MODULE_AUTOENCODER, MODULE_STRUCTURE_ENCODER, MODULE_TIMBRE_ENCODER = 0, 1, 2, 3
 CFG_AUDIO, CFG_MIDI = 0, 1
-KERNEL_CLASSES = {"tap_gemm_tc": 0, "tap_gemm_simt": 1, "attention": 2, "row_norm": 3, "act_operand": 4, "pqmf": 5}
+KERNEL_CLASSES = {"tap_gemm_tc": 0, "tap_gemm_simt": 1, "attention": 2, "row_norm": 3, "act_operand": 4, "pqmf": 5,
+                  "mlp_fused": 7}
 
 
 class AfterConfig(C.Structure):

@@ -19,7 +19,7 @@ extern std::atomic<int64_t> g_launches;
 // captured graph cannot be timed), so the numbers are per-launch durations of the very same kernels.
 enum KernelClass {
   KC_TAP_GEMM_TC = 0, KC_TAP_GEMM_SIMT = 1, KC_ATTENTION = 2, KC_ROW_NORM = 3, KC_ACT_OPERAND = 4, KC_PQMF = 5,
-  KC_OTHER = 6, KC_COUNT = 7
+  KC_OTHER = 6, KC_MLP_FUSED = 7, KC_COUNT = 8
 };
 
 struct Profiler {

@@ -291,7 +291,7 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   }
   const int clusters = std::min(std::max(p0.n_tiles, p1.n_tiles * p1.ksplit), n_pairs);
   const double rows = (double)B * T;
-  ProfScope prof(KC_TAP_GEMM_TC, st, 2.0 * rows * ((double)W0.N * W0.K + (double)W2.N * W2.K),
+  ProfScope prof(KC_MLP_FUSED, st, 2.0 * rows * ((double)W0.N * W0.K + (double)W2.N * W2.K),
                  rows * (W0.Cin * 4.0 + W0.N * 4.0 * 2 + W2.N * 8.0));
   const int smem = tc::Smem2<BN>::total(nprod > 1 ? 3 : 1);
   static int trace = -1;

@@ -317,21 +317,35 @@ def main():
         eng.sample(x0, cond, tc, NS, 2.0, 1.0)
         prof = eng.profile_read()
         eng.profile(False)
-        g = prof["tap_gemm_tc" if args.precision != "fp32_simt" else "tap_gemm_simt"]
+        tc_mode = args.precision != "fp32_simt"
+        dom = "mlp_fused" if (tc_mode and prof["mlp_fused"]["launches"]) else ("tap_gemm_tc" if tc_mode else "tap_gemm_simt")
+        g = prof[dom]
         tot_prof = sum(v["ms"] for v in prof.values())
         if g["launches"]:
             ach = g["flops"] / (g["ms"] / 1e3) / 1e12
             issued = 3 if args.precision == "fp32" else 1
+            kname = {"mlp_fused": "mlp_fused_tc2_kernel<256> (MLP up + down projection, one persistent CTA-pair tcgen05 launch)",
+                     "tap_gemm_tc": "tap_gemm_tc2_kernel (CTA-pair tcgen05 tap-GEMM)", "tap_gemm_simt": "tap_gemm_simt_kernel"}[dom]
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": "tap_gemm_tc2_kernel (CTA-pair tcgen05 tap-GEMM; class tap_gemm_tc)",
+                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": kname,
                     "launches_per_sample": g["launches"], "avg_launch_us": g["ms"] * 1e3 / g["launches"],
                     "flops_per_launch": g["flops"] / g["launches"], "share_of_profiled_ms": g["ms"] / tot_prof,
                     "issued_mma_per_product": issued, "issued_frac": ach * issued / pk["bf16_sustained"],
-                    "peak_source": pk["source"] + ", bf16 sustained"}
+                    "peak_source": pk["source"] + ", bf16 sustained",
+                    "how": "algorithmic 2*M*(N0*K0 + N2*K2) flops per launch / mean CUDA-event duration of the launches of one "
+                           "sample() call on the library's work stream (graph bypassed, PDL off between events)"}
+            if dom == "mlp_fused":
+                q = prof["tap_gemm_tc"]
+                if q["launches"]:
+                    roof["other_gemm_class"] = {"kernel": "tap_gemm_tc2_kernel (QKV + out-proj)", "launches": q["launches"],
+                                                "achieved": q["flops"] / (q["ms"] / 1e3) / 1e12,
+                                                "frac": q["flops"] / (q["ms"] / 1e3) / 1e12 / pk["bf16_sustained"]}
             tr = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tr):
                 with open(tr) as fh:
-                    roof["traffic"] = json.load(fh).get("tap_gemm_tc_kernel_bytes_per_launch")
+                    tj = json.load(fh)
+                roof["traffic"] = tj.get("tc::mlp_fused_tc2_kernel<256>_bytes_per_launch" if dom == "mlp_fused" else "tap_gemm_tc_kernel_bytes_per_launch")
+                roof["traffic_source"] = tj.get("source")
 
     # ---- CPU baseline: the oracle port of the reference sampler on this box's host cores (rank 0, N = 1 only) --------
     cpu = None

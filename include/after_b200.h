@@ -228,12 +228,14 @@ int after_ae_ratio(after_handle h);
  * events on the library's work stream and CUDA-graph replay is bypassed, so the same kernels run one by one.
  * after_profile_read synchronises the device and returns, for one class, the number of launches since
  * after_profile_enable(h, 1), their summed duration (ms) and their summed algorithmic flops / bytes. */
-#define AFTER_KERNEL_TAP_GEMM_TC 0   /* tcgen05 tap-GEMM (linears + convolutions) */
+#define AFTER_KERNEL_TAP_GEMM_TC 0   /* tcgen05 tap-GEMM (linears + convolutions), except the fused MLP */
 #define AFTER_KERNEL_TAP_GEMM_SIMT 1 /* fp32 FFMA tap-GEMM */
 #define AFTER_KERNEL_ATTENTION 2     /* banded attention + residual + AdaLN-c + LN3 */
 #define AFTER_KERNEL_ROW_NORM 3      /* AdaLN-t + LN1 */
 #define AFTER_KERNEL_ACT_OPERAND 4   /* GroupNorm/BatchNorm + Snake/SiLU operand pass */
 #define AFTER_KERNEL_PQMF 5          /* PQMF analysis / synthesis */
+#define AFTER_KERNEL_OTHER 6         /* unclassified */
+#define AFTER_KERNEL_MLP_FUSED 7     /* fused MLP (up + down projection in one persistent tcgen05 launch) */
 int after_profile_enable(after_handle h, int on);
 int after_profile_read(after_handle h, int kernel_class, int64_t* launches, double* ms, double* flops,
                        double* bytes);
