@@ -18,8 +18,7 @@ namespace after {
 
 inline void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int groups, cudaStream_t st) {
   dim3 grid(ceil_div(T, 256), B);
-  gn_stats_kernel<<<grid, 256, 0, st>>>(x, stats, T, C, groups);
-  AFTER_CUDA_CHECK(cudaGetLastError());
+  launch_k(gn_stats_kernel, grid, dim3(256), 0, st, x, stats, T, C, groups);
   AFTER_COUNT_LAUNCH();
 }
 
@@ -289,9 +288,8 @@ struct ConvNet {
     const size_t smem = (size_t)5 * C * sizeof(float);
     const double el = (double)B * T;
     ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 * C + Cp * (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
-    if (C % 4 == 0 && Cp % 4 == 0) act_operand_kernel<4><<<grid, 256, smem, st>>>(x, o, p, T, C, Cp, fpb);
-    else act_operand_kernel<1><<<grid, 256, smem, st>>>(x, o, p, T, C, Cp, fpb);
-    AFTER_CUDA_CHECK(cudaGetLastError());
+    if (C % 4 == 0 && Cp % 4 == 0) launch_k(act_operand_kernel<4>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb);
+    else launch_k(act_operand_kernel<1>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb);
     AFTER_COUNT_LAUNCH();
   }
 
@@ -460,6 +458,7 @@ struct Codec : ConvNet {
 
   // ------------------------------------------------------------------ AutoEncoder.encode
   void encode_body(const float* audio, float* z, int B, int64_t samples, cudaStream_t st) {
+    PdlScope pdl(true);  // every kernel of the codec graphs starts with pdl_wait() (common.cuh)
     begin(st);
     int T = (int)(samples / M);
     float *x = buf[0], *y1 = buf[1], *o = buf[2];
@@ -468,8 +467,8 @@ struct Codec : ConvNet {
       const size_t smem = ((size_t)pq_fwd_k * M + PQ_FRAMES * M + pq_fwd_k) * sizeof(float);
       const int p = (pq_fwd_k - 1) + 1;  // get_padding(k): left = (p - 1) / 2
       ProfScope prof(KC_PQMF, st, 2.0 * B * T * M * pq_fwd_k, (double)B * T * M * 8.0);
-      pqmf_analysis_kernel<<<grid, 256, smem, st>>>(audio, pq_fwd, x, T, pq_fwd_k, (p - 1) / 2);
-      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+      launch_k(pqmf_analysis_kernel, grid, dim3(256), smem, st, audio, pq_fwd, x, T, pq_fwd_k, (p - 1) / 2);
+      AFTER_COUNT_LAUNCH();
     }
     double* xs = new_slot();
     gn_stats_launch(x, xs, B, T, cfg.ae_in_channels, to_in.a1.groups, st);
@@ -495,8 +494,8 @@ struct Codec : ConvNet {
     conv(enc_out, B, T, o, nullptr, nullptr, 1, st);
     // ReluBottleneck is the identity at inference (SimpleNetsStream.py:753-760); public layout is channel-first
     dim3 grid(ceil_div(T, 32), ceil_div(cfg.ae_z_channels, 32), B);
-    tokens_to_channels_kernel<<<grid, 256, 0, st>>>(o, z, cfg.ae_z_channels, T);
-    AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+    launch_k(tokens_to_channels_kernel, grid, dim3(256), 0, st, o, z, (int)cfg.ae_z_channels, T);
+    AFTER_COUNT_LAUNCH();
   }
 
   // The captured graphs work on library-owned staging buffers (io_audio / io_z), so they never bake caller pointers
@@ -511,13 +510,14 @@ struct Codec : ConvNet {
 
   // ------------------------------------------------------------------ AutoEncoder.decode
   void decode_body(const float* z, float* audio, int B, int Tz, cudaStream_t st) {
+    PdlScope pdl(true);
     begin(st);
     int T = Tz;
     float *x = buf[0], *y1 = buf[1], *o = buf[2];
     {
       dim3 grid(ceil_div(T, 32), ceil_div(cfg.ae_z_channels, 32), B);
-      channels_to_frames_kernel<<<grid, 256, 0, st>>>(z, o, cfg.ae_z_channels, T);
-      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+      launch_k(channels_to_frames_kernel, grid, dim3(256), 0, st, z, o, (int)cfg.ae_z_channels, T);
+      AFTER_COUNT_LAUNCH();
     }
     NormAct ident;
     produce(o, ident, nullptr, dec_in, B, T, cfg.ae_z_channels, st);
@@ -549,8 +549,9 @@ struct Codec : ConvNet {
       dim3 grid(ceil_div(T, PS_FRAMES), B);
       const size_t smem = ((size_t)pq_inv_k * M * M + (size_t)(PS_FRAMES + pq_inv_k - 1) * M) * sizeof(float);
       ProfScope prof(KC_PQMF, st, 2.0 * B * T * M * M * pq_inv_k, (double)B * T * M * (cfg.ae_use_loudness ? 12.0 : 8.0));
-      pqmf_synthesis_kernel<<<grid, 256, smem, st>>>(o, pq_inv, audio, T, pq_inv_k, (pq_inv_k - 1) / 2, cfg.ae_use_loudness);
-      AFTER_CUDA_CHECK(cudaGetLastError()); AFTER_COUNT_LAUNCH();
+      launch_k(pqmf_synthesis_kernel, grid, dim3(256), smem, st, o, pq_inv, audio, T, pq_inv_k, (pq_inv_k - 1) / 2,
+               (int)cfg.ae_use_loudness);
+      AFTER_COUNT_LAUNCH();
     }
   }
 

@@ -57,6 +57,8 @@ __device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
 template <int VEC>
 __global__ void __launch_bounds__(256)
 act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int Cp, int frames_per_block) {
+  pdl_wait();
+  pdl_trigger();
   // Cp >= C: output channels [C, Cp) are written as zeros (operands of the few 16/32-channel layers are padded to the
   // 64-channel K granule of the tensor-core path)
   extern __shared__ float sm[];  // mu[C], rs[C], be[C], al[C], ib[C]
@@ -141,6 +143,8 @@ act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int
 // is not a tap-GEMM epilogue (PQMF output, naive-kernel layers).  grid = (ceil(T / 256), B), 256 threads.
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int T, int C, int groups) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 256;
   const int nt = min(256, T - t0);
@@ -163,6 +167,8 @@ gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int T, 
 __global__ void __launch_bounds__(256)
 channels_to_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
   __shared__ float tile[32][33];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
@@ -187,6 +193,8 @@ __global__ void __launch_bounds__(256)
 pqmf_analysis_kernel(const float* __restrict__ audio, const float* __restrict__ wT, float* __restrict__ out, int T,
                      int K, int pad_l) {
   constexpr int M = 16;
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   float* s_w = sm;                  // [K][M]
   float* s_x = sm + (size_t)K * M;  // [PQ_FRAMES * M + K]
@@ -231,6 +239,8 @@ __global__ void __launch_bounds__(256)
 pqmf_synthesis_kernel(const float* __restrict__ u, const float* __restrict__ wT, float* __restrict__ audio, int T,
                       int K, int pad_l, int loud) {
   constexpr int M = 16;
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   float* s_w = sm;                      // [K][M][M]
   float* s_x = sm + (size_t)K * M * M;  // [(PS_FRAMES + K - 1)][M]

@@ -392,6 +392,7 @@ struct Denoiser {
     const int rows = N * T;
     PdlScope pdl(true);  // every kernel below starts with pdl_wait(): programmatic dependent launches are safe
     {
+      // 4 frames per block: 16-frame blocks (4x less W_in^T traffic from L2, 128 blocks) measured 1.4 % slower
       dim3 grid(ceil_div(T, 4), n_src);
       launch_k(patch_embed_kernel<4>, grid, dim3(256), C * 4 * sizeof(float), st, x_src, pe_wt, pe_b, h0, C, T, D);
       AFTER_COUNT_LAUNCH();

@@ -983,6 +983,8 @@ cfg_combine_kernel(const float* __restrict__ proj, const float* __restrict__ gui
 __global__ void __launch_bounds__(256)
 tokens_to_channels_kernel(const float* __restrict__ proj, float* __restrict__ out, int C, int T) {
   __shared__ float tile[32][33];
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {

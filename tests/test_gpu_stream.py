@@ -163,3 +163,43 @@ def test_partial_roll_and_errors():
             off.sample_stream(torch.zeros(1, 64, 4).cuda(), torch.zeros(1, 6).cuda(), torch.zeros(1, 12, 4).cuda(), 2)
     finally:
         off.close()
+
+
+def test_streamer_runs_the_streaming_denoiser_over_consecutive_buffers():
+    """nn_tilde-shaped ``Streamer.forward`` on an engine with ``max_cache_size = LOCAL_ATTENTION_SIZE``: three consecutive
+    8192-sample buffers; the diffusion stage carries its per-step KV histories across calls exactly like the exported model
+    (export.py:398-416) while codec / encoders run block-offline.  Checked against the oracle chain with injected noise."""
+    from after_b200.engine import Engine
+    from after_b200.streamer import Streamer
+    from oracle import after_oracle as O
+    mc = config.get_config("tiny")
+    acfg = config.base_autoencoder()
+    sds = dict(den=synth.denoiser_state_dict(mc.denoiser, 1), ae=synth.autoencoder_state_dict(acfg, 2),
+               se=synth.encoder1d_state_dict(mc.structure_encoder, 3), te=synth.ecapa_state_dict(mc.timbre_encoder, 4))
+    n_sig, frames, steps = 16, 4, 3
+    eng = Engine(model=mc, autoencoder=acfg, denoiser_state=sds["den"], autoencoder_state=sds["ae"], structure_state=sds["se"],
+                 timbre_state=sds["te"], precision="fp32", max_batch=2, max_steps=steps, seq_len=n_sig,
+                 max_samples=n_sig * acfg.ratio, max_cache_size=mc.denoiser.local_attention_size)
+    try:
+        st = Streamer(eng, n_signal_timbre=n_sig, chunk_size=4)
+        st.set_nb_steps(steps); st.set_guidance_timbre(2.0); st.set_guidance_structure(1.0)
+        cache = O.StreamCache(mc.denoiser, mc.denoiser.local_attention_size)
+        hist = torch.zeros(1, 64, n_sig)
+        worst = 0.0
+        for blk in range(3):
+            audio = torch.cat([synth.synth_audio(1, frames * acfg.ratio, seed=40 + blk),
+                               synth.synth_audio(1, frames * acfg.ratio, seed=50 + blk)], 1)
+            noise = torch.randn(1, 64, frames, generator=torch.Generator().manual_seed(60 + blk))
+            got = st.forward(audio.cuda(), noise=noise)
+            z_s = O.ae_encode(sds["ae"], acfg, audio[:, :1])
+            z_t = O.ae_encode(sds["ae"], acfg, audio[:, 1:])
+            hist = torch.cat([hist, z_t], -1)[..., frames:]
+            cond = O.ecapa_forward(sds["te"], mc.timbre_encoder, hist)
+            tcond = O.encoder1d_forward(sds["se"], mc.structure_encoder, z_s)
+            x = O.sample_stream(sds["den"], mc.denoiser, cache, noise, cond, tcond, steps, 2.0, 1.0, clamp=0.1)
+            want = O.ae_decode(sds["ae"], acfg, x)
+            worst = max(worst, rel(got, want))
+        print(f"streaming streamer.forward over 3 buffers: {worst:.2e}")
+        assert worst < 1e-3
+    finally:
+        eng.close()
