@@ -945,8 +945,11 @@ __device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters
   return false;
 }
 
+// One more warp than the pair kernel: warp 2 + EPI_WARPS publishes finished up-projection tiles (see below).
+constexpr int NUM_THREADS_MLP = NUM_THREADS2 + 32;
+
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS_MLP, 1)
 mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_constant__ LinearProblem p1, int T, int nprod,
                      int m_tiles_per_b, int* __restrict__ flags, int flag_need, unsigned long long* dbg) {
   auto mark = [&](int slot) {  // profiling experiments only: per-cluster %globaltimer marks of the leader CTA
@@ -970,6 +973,7 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
   uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* pub_bar = bars + 24;  // [2]: "every epilogue warp of this CTA has stored its part of up tile ti" (parity ti & 1)
   float* epi_stage = reinterpret_cast<float*>(bars + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -988,6 +992,7 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
+      mbar_init(&pub_bar[i], EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1078,6 +1083,23 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
         umma2_commit_mc(&tmem_full[buf]);
       }
     }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // Publisher: when all epilogue warps of this CTA have stored their part of an up-projection tile (pub_bar, CTA-scope
+    // release/acquire), one thread makes those stores visible at gpu scope and bumps the row block's counter.  The
+    // epilogue warps never wait for that fence: in the in-kernel trace the former "every thread __threadfence(),
+    // bar.sync, red.release" sequence held all 16 warps for ~2.5 us after each up tile, on the path every
+    // down-projection item waits for (now ~1.2 us until the next accumulator is picked up).  Causality: stores -po->
+    // mbarrier.arrive(release.cta) -sw-> try_wait(acquire.cta) -po-> fence.acq_rel.gpu; red.release.gpu -sw-> the
+    // consumer's ld.acquire.gpu.
+    if (lane == 0) {
+      int prob, tile;
+      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile) && prob == 0; ++ti) {
+        const int mt = tile / p0.n_tiles_n;
+        mbar_wait(&pub_bar[ti & 1], (ti >> 1) & 1);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + mt) : "memory");
+      }
+    }
   } else {
     const int quad = warp & 3;
     const uint32_t te0 = mapa(smem_u32(&tmem_empty[0]), 0), te1 = mapa(smem_u32(&tmem_empty[1]), 0);
@@ -1121,12 +1143,12 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
       if (tr) mark(11 + 4 * ti);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(buf ? te1 : te0);
-      if (prob == 0) {
-        // publish: every epilogue thread's stores -> gpu scope, then one release-increment per CTA
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-        if (warp == 2 && lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + mt) : "memory");
+      if (lane == 0) {
+        // hand the stored tile to the publisher BEFORE releasing the accumulator buffer: a warp can then reach its next
+        // arrival on the same pub_bar parity (tile ti + 2, same TMEM buffer) only after every warp has arrived for ti
+        if (prob == 0)
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&pub_bar[ti & 1])) : "memory");
+        mbar_arrive_cluster(buf ? te1 : te0);
       }
       if (warp == 2 && lane == 0) mark(prob ? 6 : 5);
     }

@@ -306,7 +306,7 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
     dbg_now = dbg;
     AFTER_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 128 * 16 * sizeof(unsigned long long), st));
   }
-  launch_k(tc::mlp_fused_tc2_kernel<BN>, dim3(2 * clusters), dim3(tc::NUM_THREADS2), (size_t)smem, st, p0, p1, T, nprod,
+  launch_k(tc::mlp_fused_tc2_kernel<BN>, dim3(2 * clusters), dim3(tc::NUM_THREADS_MLP), (size_t)smem, st, p0, p1, T, nprod,
            m_tiles_per_b, flags, 2 * p0.n_tiles_n, dbg_now);
   AFTER_COUNT_LAUNCH();
   if (dbg_now) {
