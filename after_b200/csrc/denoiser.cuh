@@ -192,10 +192,10 @@ struct Denoiser {
       set((const void*)attn_chunk4_bulk_kernel<4, 20>, bytes(4, 20));
       set((const void*)attn_chunk4_bulk_kernel<4, 32>, bytes(4, 32));
       auto wbytes = [](int nh, int maxk) { return 128 + (size_t)(16 + maxk) * 2 * nh * 64 * sizeof(float); };
-      set((const void*)attn_warp_chunk_kernel<8, 12, true>, wbytes(8, 12));
-      set((const void*)attn_warp_chunk_kernel<8, 20, true>, wbytes(8, 20));
-      set((const void*)attn_warp_chunk_kernel<4, 12, true>, wbytes(4, 12));
-      set((const void*)attn_warp_chunk_kernel<4, 20, true>, wbytes(4, 20));
+      set((const void*)attn_warp_chunk_kernel<8, 12, true, 4>, wbytes(8, 12));
+      set((const void*)attn_warp_chunk_kernel<8, 20, true, 4>, wbytes(8, 20));
+      set((const void*)attn_warp_chunk_kernel<4, 12, true, 4>, wbytes(4, 12));
+      set((const void*)attn_warp_chunk_kernel<4, 20, true, 4>, wbytes(4, 20));
     }
     cacheW = c.max_cache_size;
     AFTER_REQUIRE(cacheW >= 0 && cacheW <= 64, AFTER_EINVAL, "max_cache_size must be in [0, 64]");
@@ -289,14 +289,21 @@ struct Denoiser {
     if (warp_ok && variant == 0 && T % 16 == 0) {
       const int n_seq = rows / T, chunks = n_seq * (T / 4);
       const size_t smem = 128 + (size_t)(16 + cfg.local_attention_size - 1) * 2 * D * sizeof(float);
-      launch_k(attn_warp_chunk_kernel<NH, MAXK, true>, dim3(chunks / 4), dim3(128), smem, st, qkv, h, o, adaC_step, L * 2 * D,
+      launch_k(attn_warp_chunk_kernel<NH, MAXK, true, 4>, dim3(chunks / 4), dim3(128), smem, st, qkv, h, o, adaC_step, L * 2 * D,
                l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
                mlp_flags + (size_t)l * flag_stride, flag_stride);
     } else if (warp_ok && (variant == 0 || variant == 3)) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      launch_k(attn_warp_chunk_kernel<NH, MAXK, false>, dim3(ceil_div(chunks, 4)), dim3(128), 0, st, qkv, h, o, adaC_step,
-               L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
-               mlp_flags + (size_t)l * flag_stride, flag_stride);
+      static int qpw = -1;  // AFTER_ATTN_QPW = queries per warp (4 | 2 | 1)
+      if (qpw < 0) { const char* e = getenv("AFTER_ATTN_QPW"); qpw = e ? atoi(e) : 4; }
+#define AFTER_LAUNCH_ATTN_WARP(Q)                                                                                       \
+  launch_k(attn_warp_chunk_kernel<NH, MAXK, false, Q>, dim3(ceil_div(chunks * (4 / Q), 4)), dim3(128), 0, st, qkv, h, o, \
+           adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size, \
+           mlp_flags + (size_t)l * flag_stride, flag_stride)
+      if (qpw == 2) AFTER_LAUNCH_ATTN_WARP(2);
+      else if (qpw == 1) AFTER_LAUNCH_ATTN_WARP(1);
+      else AFTER_LAUNCH_ATTN_WARP(4);
+#undef AFTER_LAUNCH_ATTN_WARP
     } else if (cfg.attention_chunk_size == 4 && variant == 2) {
       const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
       const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;

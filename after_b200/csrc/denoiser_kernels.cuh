@@ -424,8 +424,8 @@ attn_chunk4_bulk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
 // shared memory.  With 10 warps per SM (one wave) the direct-load version is bound by exposed L2 latency
 // (ncu: 5.3 long-scoreboard stall cycles per issue at 2.5 warps per scheduler); staging exposes ONE round trip and
 // reads every key row once per 16 queries instead of once per 4.
-template <int NH, int MAXK, bool STAGED>
-__global__ void __launch_bounds__(128, NH == 8 ? 3 : 4)
+template <int NH, int MAXK, bool STAGED, int QPW>
+__global__ void __launch_bounds__(128, QPW == 4 ? (NH == 8 ? 3 : 4) : QPW == 2 ? (NH == 8 ? 4 : 6) : (NH == 8 ? 5 : 8))
 attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
                        const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
@@ -446,7 +446,11 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
   pdl_wait();
   pdl_trigger();
   if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
-  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // QPW queries per warp: 4 = the whole chunk; 2 / 1 = the chunk's queries are spread over 2 / 4 warps (key rows are
+  // then re-read through L1, but each warp's dependent chain is shorter and more warps are resident)
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int chunk = wg / (4 / QPW);
+  const int rbase = (wg % (4 / QPW)) * QPW;
   int srow0 = 0;  // first key row held in shared memory
   if (STAGED) {
     const int chunk_b = blockIdx.x * 4;  // the block's chunks lie in one sequence (T % 16 == 0)
@@ -479,11 +483,11 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
   const int eoff = hd * 64 + dq * 4;  // element offset of float4 group 0 inside a row; group i adds 4 * LPH * i
 
   // ---- queries (scaled into the log2 domain) -----------------------------------------------------------------
-  float4 q[4][F];
+  float4 q[QPW][F];
   const float qs = 0.125f * 1.4426950408889634f;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int t = min(c0 + r, T - 1);  // ragged last chunk: surplus rows recompute the last one and are not stored
+  for (int r = 0; r < QPW; ++r) {
+    const int t = min(c0 + rbase + r, T - 1);  // ragged last chunk: surplus rows recompute the last one and are not stored
     const float* qp = qkv + ((size_t)n * T + t) * (3 * D) + eoff;
 #pragma unroll
     for (int i = 0; i < F; ++i) {
@@ -504,55 +508,55 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
           : "=r"(ok) : "r"(bar_s) : "memory");
     }
   }
-  float sc[4][MAXK];
+  float sc[QPW][MAXK];
 #pragma unroll
   for (int j = 0; j < MAXK; ++j) {
-    float2 acc[4];
+    float2 acc[QPW];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < QPW; ++r) acc[r] = make_float2(0.f, 0.f);
     if (j < nk) {
       const float* kp = kbase + (size_t)j * kstride;
 #pragma unroll
       for (int i = 0; i < F; ++i) {
         const float4 k = *reinterpret_cast<const float4*>(kp + 4 * LPH * i);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < QPW; ++r) {
           acc[r] = __ffma2_rn(make_float2(q[r][i].x, q[r][i].y), make_float2(k.x, k.y), acc[r]);
           acc[r] = __ffma2_rn(make_float2(q[r][i].z, q[r][i].w), make_float2(k.z, k.w), acc[r]);
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < QPW; ++r) {
       float v = acc[r].x + acc[r].y;
 #pragma unroll
       for (int o = 1; o < LPH; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       // key ks0 + j is visible to query c0 + r iff it is not older than the window (all keys of the chunk are visible)
-      const int ks = min(c0, max(0, c0 + r - window + 1));
+      const int ks = min(c0, max(0, c0 + rbase + r - window + 1));
       sc[r][j] = (j < nk && ks0 + j >= ks) ? v : -INFINITY;
     }
   }
   // ---- softmax (log2 domain) and P.V ---------------------------------------------------------------------------
-  float m[4], l[4];
+  float m[QPW], l[QPW];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < QPW; ++r) {
     m[r] = sc[r][0];
 #pragma unroll
     for (int j = 1; j < MAXK; ++j) m[r] = fmaxf(m[r], sc[r][j]);
     l[r] = 0.f;
   }
-  float4 o[4][F];
+  float4 o[QPW][F];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < QPW; ++r)
 #pragma unroll
     for (int i = 0; i < F; ++i) o[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* vbase = kbase + D;
 #pragma unroll
   for (int j = 0; j < MAXK; ++j) {
     if (j < nk) {
-      float p[4];
+      float p[QPW];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < QPW; ++r) {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[r]) : "f"(sc[r][j] - m[r]));  // 2^(-inf) = 0 for masked keys
         l[r] += p[r];
       }
@@ -561,7 +565,7 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
       for (int i = 0; i < F; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(vp + 4 * LPH * i);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < QPW; ++r) {
           const float2 pp = make_float2(p[r], p[r]);
           float2 a = __ffma2_rn(pp, make_float2(v.x, v.y), make_float2(o[r][i].x, o[r][i].y));
           float2 b = __ffma2_rn(pp, make_float2(v.z, v.w), make_float2(o[r][i].z, o[r][i].w));
@@ -581,8 +585,8 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
     bb[i] = *reinterpret_cast<const float4*>(b3 + eoff + 4 * LPH * i);
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int t = min(c0 + r, T - 1);
+  for (int r = 0; r < QPW; ++r) {
+    const int t = min(c0 + rbase + r, T - 1);
     const size_t roff = ((size_t)n * T + t) * D + eoff;
     const float inv = 1.0f / l[r];
     float x[4 * F];
@@ -610,7 +614,7 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
       x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al[i].w) + be[i].w;
       s1 += (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
     }
-    const bool store = c0 + r < T;
+    const bool store = c0 + rbase + r < T;
     if (store) {
 #pragma unroll
       for (int i = 0; i < F; ++i)

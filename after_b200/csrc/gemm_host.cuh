@@ -281,7 +281,9 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   p1.a_hi = m1.hi; p1.a_lo = m1.lo; p1.b_hi = W2.map2_hi; p1.b_lo = W2.map2_lo; p1.epi = epi1; p1.Cin = W2.Cin;
   p1.n_tiles_n = W2.N / BN; p1.n_tiles = p1.n_tiles_n * n_m_tiles;
   p0.ksplit = 1; p1.ksplit = 1;
-  if (partial && mlp_ksplit() == 2 && !epi1.out_hi && epi1.out_f32 && (W2.Cin / tc::BK) % 2 == 0) {
+  // only when the down projection has too few tiles to fill the machine (48 tiles on 74 CTA pairs at base B=8): with
+  // many waves of tiles the split buys no balance and costs one extra write + read of the partial tensor
+  if (partial && mlp_ksplit() == 2 && !epi1.out_hi && epi1.out_f32 && (W2.Cin / tc::BK) % 2 == 0 && p1.n_tiles < 2 * n_pairs) {
     p1.ksplit = 2;
     p1.epi2 = GemmEpi{};
     p1.epi2.out_f32 = partial;
