@@ -58,6 +58,10 @@ struct Denoiser {
   float *kcache = nullptr, *vcache = nullptr;   // [max_steps][L][maxN][cacheW][D]
   float* qkv_stream = nullptr;                  // [L][maxRows][3D]
   int last_N = 0, last_T = 0;
+  // skinny path of small streaming blocks (rows <= SKINNY_ROWS): fp32 operand rows for skinny_linear_kernel
+  static constexpr int SKINNY_ROWS = 16;
+  float *sk_a = nullptr, *sk_hid = nullptr;     // [SKINNY_ROWS][D], [SKINNY_ROWS][HID]
+  bool skinny_now = false;
 
   // graph cache
   struct GraphEntry {
@@ -206,6 +210,10 @@ struct Denoiser {
       qkv_stream = arena->alloc<float>((size_t)L * maxRows * 3 * D);
       AFTER_CUDA_CHECK(cudaMemset(kcache, 0, cache_floats * sizeof(float)));
       AFTER_CUDA_CHECK(cudaMemset(vcache, 0, cache_floats * sizeof(float)));
+      sk_a = arena->alloc<float>((size_t)SKINNY_ROWS * D);
+      sk_hid = arena->alloc<float>((size_t)SKINNY_ROWS * HID);
+      AFTER_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<SKINNY_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float))));
     }
     const char* ng = getenv("AFTER_NO_GRAPH");
     use_graph = !(ng && ng[0] == '1');
@@ -226,8 +234,16 @@ struct Denoiser {
   }
   RowOperandOut operand_out(const ActOperand& o) const {
     RowOperandOut r;
+    if (skinny_now) { r.f32 = sk_a; return r; }  // the skinny linears read fp32 rows
     r.f32 = o.f32; r.hi = o.hi; r.lo = nprod() > 1 ? o.lo : nullptr;
     return r;
+  }
+  // out[M, N] = act(A[M, K] W^T + bias) (+ res), M <= SKINNY_ROWS (skinny_linear_kernel)
+  void skinny(const float* A, const GemmWeight& w, const float* res, float* out, int M, int gelu, cudaStream_t st) {
+    ProfScope prof(KC_TAP_GEMM_SIMT, st, 2.0 * M * w.N * w.K, (double)w.N * w.K * 4.0);
+    launch_k(skinny_linear_kernel<SKINNY_ROWS>, dim3(ceil_div(w.N, 8)), dim3(256), (size_t)M * w.K * sizeof(float), st, A, w.w,
+             w.bias, res, out, w.N, M, w.N, w.K, gelu);
+    AFTER_COUNT_LAUNCH();
   }
   // small fp32 linears that run once per call (tables): C[M,N] = A[M,K] W[N,K]^T + bias
   void small_linear(const float* A, const float* W, const float* bias, float* Cout, int M, int N, int K, int gelu,
@@ -344,7 +360,7 @@ struct Denoiser {
     ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
     const size_t off = (size_t)cache_index * cache_slab() + (size_t)l * maxN * cacheW * D;
-    launch_k(attn_stream_kernel<NH, MAXK>, dim3(ceil_div(rows, 4)), dim3(128), 0, st, qkv_stream + (size_t)l * maxRows * 3 * D,
+    launch_k(attn_stream_kernel<NH, MAXK>, dim3(rows), dim3(NH * 32), 0, st, qkv_stream + (size_t)l * maxRows * 3 * D,
              kcache + off, vcache + off, cacheW, rope_tab, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g,
              layers[l].n3_b, rows, T, cfg.attention_chunk_size, cfg.local_attention_size,
              mlp_flags + (size_t)l * flag_stride, flag_stride);
@@ -398,6 +414,9 @@ struct Denoiser {
                    int cache_index = -1) {
     const int rows = N * T;
     PdlScope pdl(true);  // every kernel below starts with pdl_wait(): programmatic dependent launches are safe
+    // a live streaming block is a dozen rows: weight-streaming fp32 linears instead of 256-row tensor-core tiles
+    skinny_now = cache_index >= 0 && rows <= SKINNY_ROWS && sk_a != nullptr;
+    struct Reset { bool& f; ~Reset() { f = false; } } reset_skinny{skinny_now};
     {
       // 4 frames per block: 16-frame blocks (4x less W_in^T traffic from L2, 128 blocks) measured 1.4 % slower
       dim3 grid(ceil_div(T, 4), n_src);
@@ -416,11 +435,19 @@ struct Denoiser {
         gemm(layers[l].qkv, a_op, N, T, e, st);
         attn(l, adaC_step, rows, T, st);
       } else {  // keys are cached un-rotated: plain epilogue into this layer's slot, rotation inside the attention kernel
-        GemmEpi e; e.out_f32 = qkv_stream + (size_t)l * maxRows * 3 * D; e.ldo = 3 * D;
-        gemm(layers[l].qkv, a_op, N, T, e, st);
+        float* q_l = qkv_stream + (size_t)l * maxRows * 3 * D;
+        if (skinny_now) {
+          skinny(sk_a, layers[l].qkv, nullptr, q_l, rows, 0, st);
+        } else {
+          GemmEpi e; e.out_f32 = q_l; e.ldo = 3 * D;
+          gemm(layers[l].qkv, a_op, N, T, e, st);
+        }
         attn_stream(l, cache_index, adaC_step, rows, T, st);
       }
-      {
+      if (skinny_now) {
+        skinny(sk_a, layers[l].mlp0, nullptr, sk_hid, rows, 1, st);
+        skinny(sk_hid, layers[l].mlp2, h, h, rows, 0, st);
+      } else {
         GemmEpi e0; e0.ldo = HID; e0.gelu = 1;
         e0.out_f32 = hid_op.f32; e0.out_hi = hid_op.hi; e0.out_lo = nprod() > 1 ? hid_op.lo : nullptr;
         GemmEpi e1; e1.out_f32 = h; e1.ldo = D; e1.res = h;
@@ -434,7 +461,9 @@ struct Denoiser {
         }
       }
     }
-    {
+    if (skinny_now) {
+      skinny(h, out_proj, nullptr, proj, rows, 0, st);
+    } else {
       GemmEpi e; e.out_f32 = proj; e.ldo = C;
       if (!tc_mode()) {  // fp32 mode: the operand is h itself
         ActOperand hop; hop.f32 = h; hop.capacity = (size_t)maxRows * D;

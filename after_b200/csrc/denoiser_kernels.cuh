@@ -736,51 +736,55 @@ attn_adaln_c_ln3_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
 // position p = W + t of it, the band is the same index arithmetic over that longer sequence, and RoPE is applied
 // here (queries at p, keys at their position in history + block) because the history is cached UN-rotated and
 // every roll shifts its positions.  qkv holds the plain projection of this block; kc / vc: [n][W][D] of this
-// (diffusion step, layer).  Same warp-per-token layout and same tail (residual, AdaLN-c, LN3) as the kernel above;
-// lanes 0..15 own exactly the 16 interleaved rotary pairs of each head (dims 2 lane, 2 lane + 1 < 32).
+// (diffusion step, layer).  Same tail (residual, AdaLN-c, LN3) as the kernels above.
 // -------------------------------------------------------------------------------------------
 template <int NH, int MAXK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NH * 32)
 attn_stream_kernel(const float* __restrict__ qkv, const float* __restrict__ kc, const float* __restrict__ vc, int W,
                    const float2* __restrict__ rope_tab, float* h, RowOperandOut a_out,
                    const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
                    const float* __restrict__ g3, const float* __restrict__ b3, int n_rows, int T, int chunk, int window,
                    int* zero_flags, int n_zero) {
+  // Block = one token, warp = head (a streaming block has 3 B x T = 12 rows at B = 1, T = 4: one warp per token walking
+  // all heads took 86 us per launch, 54 % of a streaming step); lane owns dims (2 lane, 2 lane + 1) of its head, so
+  // lanes 0..15 hold exactly the 16 interleaved rotary pairs.  Warp 0 then normalises the row from shared memory.
   constexpr int D = NH * 64;
+  constexpr int NV = D / 32;
+  __shared__ __align__(16) float xs[D];
   pdl_wait();
   pdl_trigger();
   if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x;
+  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = row / T, t = row - n * T;
-  const int p = W + t, Lk = W + T;
-  const int c0 = (p / chunk) * chunk;
-  const int ce = min(c0 + chunk, Lk);
-  const int ks = min(c0, max(0, p - window + 1));
-  const int nk = ce - ks;  // <= chunk + window - 1 <= MAXK
-  const float* qrow = qkv + (size_t)row * (3 * D);
-  const float* kcn = kc + (size_t)n * W * D;
-  const float* vcn = vc + (size_t)n * W * D;
-  const float* kblk = qkv + (size_t)n * T * (3 * D) + D;  // block frame j: kblk + j * 3D ; value: + D more
-  const bool rot = lane < 16;
-  const float scale = 0.125f;  // 1/sqrt(64)
-  float2 cq = make_float2(1.f, 0.f);
-  if (rot) cq = rope_tab[p * 16 + lane];
-
-  float x[NH * 2];
-#pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    float2 q = *reinterpret_cast<const float2*>(qrow + hd * 64 + 2 * lane);
-    q = make_float2(q.x * cq.x - q.y * cq.y, q.y * cq.x + q.x * cq.y);
+  {
+    const int p = W + t, Lk = W + T;
+    const int c0 = (p / chunk) * chunk;
+    const int ce = min(c0 + chunk, Lk);
+    const int ks = min(c0, max(0, p - window + 1));
+    const int nk = ce - ks;  // <= chunk + window - 1 <= MAXK
+    const float* qrow = qkv + (size_t)row * (3 * D) + hd * 64 + 2 * lane;
+    const float* kcn = kc + (size_t)n * W * D + hd * 64 + 2 * lane;
+    const float* vcn = vc + (size_t)n * W * D + hd * 64 + 2 * lane;
+    const float* kblk = qkv + (size_t)n * T * (3 * D) + D + hd * 64 + 2 * lane;  // block frame j: + j * 3D ; value: + D more
+    const bool rot = lane < 16;
+    float2 q = *reinterpret_cast<const float2*>(qrow);
+    if (rot) {
+      const float2 cq = rope_tab[p * 16 + lane];
+      q = make_float2(q.x * cq.x - q.y * cq.y, q.y * cq.x + q.x * cq.y);
+    }
     float s[MAXK];
+    float2 vv[MAXK];
 #pragma unroll
     for (int j = 0; j < MAXK; ++j) {
       s[j] = 0.f;
+      vv[j] = make_float2(0.f, 0.f);
       if (j < nk) {
         const int kp = ks + j;
         const float* kr = kp < W ? kcn + (size_t)kp * D : kblk + (size_t)(kp - W) * (3 * D);
-        float2 k = *reinterpret_cast<const float2*>(kr + hd * 64 + 2 * lane);
+        const float* vr = kp < W ? vcn + (size_t)kp * D : kblk + D + (size_t)(kp - W) * (3 * D);
+        float2 k = *reinterpret_cast<const float2*>(kr);
+        vv[j] = *reinterpret_cast<const float2*>(vr);
         if (rot) {
           const float2 cs = rope_tab[kp * 16 + lane];
           k = make_float2(k.x * cs.x - k.y * cs.y, k.y * cs.x + k.x * cs.y);
@@ -789,7 +793,7 @@ attn_stream_kernel(const float* __restrict__ qkv, const float* __restrict__ kc, 
       }
     }
 #pragma unroll
-    for (int j = 0; j < MAXK; ++j) s[j] = warp_sum(s[j]) * scale;
+    for (int j = 0; j < MAXK; ++j) s[j] = warp_sum(s[j]) * 0.125f;  // 1/sqrt(64)
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXK; ++j) if (j < nk) m = fmaxf(m, s[j]);
@@ -800,46 +804,48 @@ attn_stream_kernel(const float* __restrict__ qkv, const float* __restrict__ kc, 
       if (j < nk) {
         const float pr = expf(s[j] - m);
         l += pr;
-        const int kp = ks + j;
-        const float* vr = kp < W ? vcn + (size_t)kp * D : kblk + D + (size_t)(kp - W) * (3 * D);
-        const float2 v = *reinterpret_cast<const float2*>(vr + hd * 64 + 2 * lane);
-        o.x = fmaf(pr, v.x, o.x);
-        o.y = fmaf(pr, v.y, o.y);
+        o.x = fmaf(pr, vv[j].x, o.x);
+        o.y = fmaf(pr, vv[j].y, o.y);
       }
     }
     const float inv = 1.0f / l;
     const float2 r = *reinterpret_cast<const float2*>(h + (size_t)row * D + hd * 64 + 2 * lane);
-    x[2 * hd] = r.x + o.x * inv;
-    x[2 * hd + 1] = r.y + o.y * inv;
+    *reinterpret_cast<float2*>(xs + hd * 64 + 2 * lane) = make_float2(r.x + o.x * inv, r.y + o.y * inv);
+  }
+  __syncthreads();
+  if (hd != 0) return;
+  float x[NV];
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + (i * 32 + lane) * 4);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
   }
   float mean, rstd;
-  row_stats<NH * 2>(x, D, mean, rstd);
+  row_stats<NV>(x, D, mean, rstd);
   const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
 #pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    const int e = hd * 64 + 2 * lane;
-    const float2 al = *reinterpret_cast<const float2*>(ap + e);
-    const float2 be = *reinterpret_cast<const float2*>(ap + D + e);
-    x[2 * hd] = (x[2 * hd] - mean) * rstd * (1.f + al.x) + be.x;
-    x[2 * hd + 1] = (x[2 * hd + 1] - mean) * rstd * (1.f + al.y) + be.y;
-    *reinterpret_cast<float2*>(h + (size_t)row * D + e) = make_float2(x[2 * hd], x[2 * hd + 1]);
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 al = *reinterpret_cast<const float4*>(ap + e);
+    const float4 be = *reinterpret_cast<const float4*>(ap + D + e);
+    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
+    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
+    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
+    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
+    *reinterpret_cast<float4*>(h + (size_t)row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
   }
-  row_stats<NH * 2>(x, D, mean, rstd);
+  row_stats<NV>(x, D, mean, rstd);
 #pragma unroll
-  for (int hd = 0; hd < NH; ++hd) {
-    const int e = hd * 64 + 2 * lane;
-    const float2 g = *reinterpret_cast<const float2*>(g3 + e);
-    const float2 b = *reinterpret_cast<const float2*>(b3 + e);
-    const float ox = (x[2 * hd] - mean) * rstd * g.x + b.x;
-    const float oy = (x[2 * hd + 1] - mean) * rstd * g.y + b.y;
-    const size_t off = (size_t)row * D + e;
-    if (a_out.f32) *reinterpret_cast<float2*>(a_out.f32 + off) = make_float2(ox, oy);
-    if (a_out.hi) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(ox, h0, l0); split_bf16(oy, h1, l1);
-      *reinterpret_cast<uint32_t*>(a_out.hi + off) = pack_bf16x2(h0, h1);
-      if (a_out.lo) *reinterpret_cast<uint32_t*>(a_out.lo + off) = pack_bf16x2(l0, l1);
-    }
+  for (int i = 0; i < NV / 4; ++i) {
+    const int e = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(g3 + e);
+    const float4 bb = *reinterpret_cast<const float4*>(b3 + e);
+    float4 ov;
+    ov.x = (x[4 * i + 0] - mean) * rstd * g.x + bb.x;
+    ov.y = (x[4 * i + 1] - mean) * rstd * g.y + bb.y;
+    ov.z = (x[4 * i + 2] - mean) * rstd * g.z + bb.z;
+    ov.w = (x[4 * i + 3] - mean) * rstd * g.w + bb.w;
+    store_operand4(a_out, (size_t)row * D + e, ov);
   }
 }
 
@@ -858,6 +864,56 @@ kv_roll_kernel(float* kc, float* vc, const float* __restrict__ qkv_stream, int m
       const int src = j + r;
       c[(size_t)j * D + d] = src < W ? c[(size_t)src * D + d] : last[(size_t)(src - W) * (3 * D) + d];
     }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Skinny linear for the streaming path: out[m, n] = act(sum_k A[m, k] W[n, k] + bias[n]) (+ res[m, n]) with M <= MAXM
+// rows (a live block is 3 CFG rows x 4 frames = 12 rows).  A 256-row tcgen05 tile would spend > 95 % of its MMAs on
+// zero rows and its fixed costs (TMEM, TMA ring, 18 tiles on 74 CTA pairs) dominate: 16 / 42 us for the QKV / MLP launches
+// of a 12-row block.  This is weight streaming instead: the whole A (<= 96 KB) sits in shared memory, every warp owns one
+// output column and reads its weight row once, coalesced, in exact fp32 (no bf16 split needed), lanes split K, and
+// after the warp reductions lane m finishes row m.  grid = N / 8 blocks of 8 warps: the weight matrix is read exactly once.
+// -------------------------------------------------------------------------------------------
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                     const float* res, float* out, int ldo, int M, int N, int K, int gelu) {
+  extern __shared__ __align__(16) float sk_as[];  // [M][K]
+  pdl_wait();
+  pdl_trigger();
+  for (int i = threadIdx.x * 4; i < M * K; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sk_as + i) = *reinterpret_cast<const float4*>(A + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+  const float* wr = W + (size_t)n * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 w = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < M) {
+        const float4 a = *reinterpret_cast<const float4*>(sk_as + m * K + k);
+        acc[m] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[m]))));
+      }
+    }
+  }
+  float v = 0.f;
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) {
+    const float t = warp_sum(acc[m]);
+    if (lane == m) v = t;
+  }
+  if (lane < M) {
+    if (bias) v += bias[n];
+    if (gelu) v = gelu_erf(v);
+    const size_t o = (size_t)lane * ldo + n;
+    if (res) v += res[o];
+    out[o] = v;
   }
 }
 

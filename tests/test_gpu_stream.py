@@ -203,3 +203,28 @@ def test_streamer_runs_the_streaming_denoiser_over_consecutive_buffers():
         assert worst < 1e-3
     finally:
         eng.close()
+
+
+def test_two_streams_stream_independently():
+    """B = 2 streaming streams on one engine (6 CFG rows, own histories per row) give, stream by stream, exactly what two
+    single-stream engines give -- the reference allows it too (max_batch_size = 4 rows, transformerv2.py:131)."""
+    cfg = config.get_config("tiny").denoiser
+    W = cfg.local_attention_size
+    eng2, _, _ = make_engine("tiny", 83, "fp32", 4, W, max_batch=2, max_steps=2)
+    engs = [make_engine("tiny", 83, "fp32", 4, W, max_batch=1, max_steps=2)[0] for _ in range(2)]
+    try:
+        gen = torch.Generator().manual_seed(17)
+        for blk in range(4):
+            x0 = torch.randn(2, cfg.n_channels, 4, generator=gen).cuda()
+            cond = torch.randn(2, cfg.cond_dim, generator=gen).cuda()
+            tc = torch.randn(2, cfg.tcond_dim, 4, generator=gen).cuda()
+            both = eng2.sample_stream(x0, cond, tc, 2, 2.0, 1.0)
+            for s in range(2):
+                one = engs[s].sample_stream(x0[s:s + 1].contiguous(), cond[s:s + 1].contiguous(), tc[s:s + 1].contiguous(), 2, 2.0, 1.0)
+                # 24 rows run on the tensor-core tiles (bf16x3), 12 rows on the exact-fp32 skinny linears: same values to
+                # fp32-mode accuracy, not bitwise
+                assert rel(both[s:s + 1], one) < 1e-4, (blk, s)
+    finally:
+        eng2.close()
+        for e in engs:
+            e.close()
