@@ -137,6 +137,23 @@ class Engine:
         self.has_structure = structure_state is not None
         self.has_timbre = timbre_state is not None
 
+    @classmethod
+    def from_run(cls, folder: str, step: Optional[int] = None, codec_ts: Optional[str] = None,
+                 autoencoder_state: Optional[Dict[str, torch.Tensor]] = None,
+                 autoencoder: Optional[AutoEncoderConfig] = None, **kwargs) -> "Engine":
+        """Engine from a reference training run folder (``config.gin`` + ``checkpoint<step>_EMA.pt``), the way
+        ``after_scripts/export.py:52-101`` instantiates the model; the codec comes from an exported ``.ts``
+        (``codec_ts``) or an ``AutoEncoder`` state dict.  ``kwargs`` go to the constructor (precision, max_batch, ...)."""
+        from . import checkpoint as ck
+        run = ck.load_run(folder, step)
+        if codec_ts is not None:
+            autoencoder_state = ck.codec_state_from_torchscript(codec_ts)
+        if autoencoder_state is not None and autoencoder is None:
+            autoencoder = ck.autoencoder_config_from_state(autoencoder_state)
+        return cls(model=run["model"], autoencoder=autoencoder, denoiser_state=run["denoiser_state"],
+                   autoencoder_state=autoencoder_state, structure_state=run["structure_state"],
+                   timbre_state=run["timbre_state"], **kwargs)
+
     # ------------------------------------------------------------------ plumbing
     def _load(self, module: int, sd: Dict[str, torch.Tensor]):
         for key, t in sd.items():
