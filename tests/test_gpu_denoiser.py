@@ -191,3 +191,28 @@ def test_degenerate_lengths(frames):
         assert rel(got, want) < 2e-4
     finally:
         eng.close()
+
+
+def test_engine_from_run_folder(tmp_path):
+    """A reference-style run folder (operative config.gin + checkpoint<step>_EMA.pt with net./encoder./encoder_time. keys,
+    model.py:144-176, 264-265) loads into an Engine and samples like the oracle with the same weights."""
+    from after_b200.engine import Engine
+    from oracle import after_oracle as O
+    from test_checkpoint import OPERATIVE  # tests/ is on sys.path (rootdir-relative "prepend" import mode)
+    mc = config.get_config("tiny")
+    den = synth.denoiser_state_dict(mc.denoiser, 5)
+    state = {"net." + k: v for k, v in den.items()}
+    state.update({"encoder." + k: v for k, v in synth.ecapa_state_dict(mc.timbre_encoder, 6).items()})
+    state.update({"encoder_time." + k: v for k, v in synth.encoder1d_state_dict(mc.structure_encoder, 7).items()})
+    run = tmp_path / "run"
+    run.mkdir()
+    torch.save({"model_state": state, "opt_state": {}}, run / "checkpoint500_EMA.pt")
+    (run / "config.gin").write_text(OPERATIVE)
+    eng = Engine.from_run(str(run), precision="fp32", max_batch=2, max_steps=3, seq_len=16)
+    try:
+        assert eng.has_denoiser and eng.has_structure and eng.has_timbre and not eng.has_codec
+        x0, cond, tc = synth.synth_inputs(2, mc.denoiser, seed=9, frames=16)
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 3, 2.0, 1.0)
+        assert rel(got, O.sample(den, mc.denoiser, x0, cond, tc, 3, 2.0, 1.0)) < TOL["fp32"]
+    finally:
+        eng.close()
