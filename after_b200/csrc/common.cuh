@@ -106,16 +106,28 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + erf_x);
 }
 // Two GELUs at once with Blackwell's packed fp32x2 FMA/MUL/ADD (half the issue slots of the scalar version).
+// (u >= 1 and -z^2 log2 e <= 0 always, so the bare MUFU approximations need none of the range fix-ups that
+// __fdividef / exp2f wrap around them: the epilogue is issue-bound, every instruction per element counts.)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
   const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
   const float2 u = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
-  const float2 t = make_float2(__fdividef(1.0f, u.x), __fdividef(1.0f, u.y));
+  const float2 t = make_float2(rcp_approx(u.x), rcp_approx(u.y));
   float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
   p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
   p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
   p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
   const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));  // -z^2 log2(e)
-  const float2 e = make_float2(exp2f(a.x), exp2f(a.y));
+  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
   const float2 erfc_z = __fmul2_rn(__fmul2_rn(p, t), e);
   const float2 erf_abs = __ffma2_rn(erfc_z, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
   const float2 erf_x = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));

@@ -407,7 +407,11 @@ __device__ __forceinline__ void split4_bf16(const float4& x, uint2& hi, uint2& l
 constexpr int EPI_STAGE_BYTES = 32 * 16 * 4;  // per warp
 constexpr int EPI_WARPS = 16;                 // warps 2..17: TMEM lane quarter = warp & 3, column quarter = (warp - 2) >> 2
 
-template <int MODE>
+// OUT: which outputs exist, when the caller knows (bit 0 fp32, bit 1 bf16 hi, bit 2 bf16 lo; -1 = look at the
+// pointers at run time); FULL: all 32 rows are valid.  Both only remove per-row pointer tests / row predicates: at 16
+// epilogue warps per SM this code is issue-bound (SASS: 535 instructions per half-block in the GELU flavour before,
+// ~40 % of them tests, selects and address arithmetic), so instructions per element are what sets its duration.
+template <int MODE, int OUT = -1, bool FULL = false>
 __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const uint32_t* v, const EpiAux& aux, float4 bias4, int b,
                                           int t_base, int T, int col0, int lane) {
 #pragma unroll
@@ -422,9 +426,12 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
   const bool has_res = MODE == EPI_PLAIN && e.res != nullptr;
   const size_t off0 = ((size_t)b * T + t_base + rsub) * e.ldo + col;
   const size_t step = (size_t)8 * e.ldo;
-  float* pf = e.out_f32 ? e.out_f32 + off0 : nullptr;
-  __nv_bfloat16* ph = e.out_hi ? e.out_hi + off0 : nullptr;
-  __nv_bfloat16* pl = e.out_lo ? e.out_lo + off0 : nullptr;
+  const bool has_f = OUT < 0 ? e.out_f32 != nullptr : (OUT & 1) != 0;
+  const bool has_h = OUT < 0 ? e.out_hi != nullptr : (OUT & 2) != 0;
+  const bool has_l = OUT < 0 ? e.out_lo != nullptr : (OUT & 4) != 0;
+  float* pf = has_f ? e.out_f32 + off0 : nullptr;
+  __nv_bfloat16* ph = has_h ? e.out_hi + off0 : nullptr;
+  __nv_bfloat16* pl = has_l ? e.out_lo + off0 : nullptr;
   float ssum = 0.f, ssq = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -442,22 +449,22 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
       x.z = a1 * cs.z - b1 * cs.w; x.w = b1 * cs.z + a1 * cs.w;
     }
     if (has_res) { x.x += aux.a[i].x; x.y += aux.a[i].y; x.z += aux.a[i].z; x.w += aux.a[i].w; }
-    if (r < nvalid && !(e.debug_skip & 1)) {
+    if ((FULL || r < nvalid) && !(e.debug_skip & 1)) {
       if (MODE == EPI_PLAIN) {
         ssum += (x.x + x.y) + (x.z + x.w);
         ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
       }
-      if (pf) *reinterpret_cast<float4*>(pf) = x;
-      if (ph) {
+      if (has_f) *reinterpret_cast<float4*>(pf) = x;
+      if (has_h) {
         uint2 hi, lo;
         split4_bf16(x, hi, lo);
         *reinterpret_cast<uint2*>(ph) = hi;
-        if (pl) *reinterpret_cast<uint2*>(pl) = lo;
+        if (has_l) *reinterpret_cast<uint2*>(pl) = lo;
       }
     }
-    if (pf) pf += step;
-    if (ph) ph += step;
-    if (pl) pl += step;
+    if (has_f) pf += step;
+    if (has_h) ph += step;
+    if (has_l) pl += step;
   }
   if (MODE == EPI_PLAIN && e.stats) {
     // fold the 8 row sub-lanes (xor 4, 8, 16) and the neighbouring 4-column lane (xor 1): lanes 0 and 2 then hold the
@@ -879,7 +886,9 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           uint32_t v[16];
           tmem_ld16_issue(taddr + c, v);
           tmem_ld_wait();
-          epi_block<MODE>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          constexpr int OUTS = MODE == EPI_ROPE ? 1 : -1;  // the RoPE flavour only ever writes the fp32 QKV buffer
+          if (T - t_base >= 32) epi_block<MODE, OUTS, true>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          else epi_block<MODE, OUTS, false>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1135,8 +1144,16 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
           tmem_ld16_issue(taddr + c, v);
           tmem_ld_wait();
           if (tr && c == cbeg) mark(9 + 4 * ti);
-          if (prob == 0) epi_block<EPI_GELU>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
-          else epi_block<EPI_PLAIN>(pe1, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          const bool full = T - t_base >= 32;
+          if (prob == 0) {  // hidden activations: bf16 hi (+ lo in the 3-product mode), never fp32 (launch_mlp_fused)
+            if (full && nprod > 1) epi_block<EPI_GELU, 6, true>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+            else if (full) epi_block<EPI_GELU, 2, true>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+            else epi_block<EPI_GELU>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          } else if (full) {
+            epi_block<EPI_PLAIN, -1, true>(pe1, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          } else {
+            epi_block<EPI_PLAIN>(pe1, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+          }
           if (tr && c == cbeg) mark(10 + 4 * ti);
         }
       }
