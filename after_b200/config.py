@@ -89,6 +89,23 @@ class EcapaConfig:
 
 
 @dataclass
+class UNetConfig:
+    """``UNET1D`` constructor arguments (after/diffusion/networks/unet1d.py:255-268) -- the conv denoiser no shipped config
+    binds.  Only the oracle covers it so far."""
+    in_size: int = 64
+    out_size: Optional[int] = None
+    channels: List[int] = field(default_factory=lambda: [128, 128, 256, 256])
+    ratios: List[int] = field(default_factory=lambda: [2, 2, 2])  # len(channels) - 1 entries are used (a leading 1 is added)
+    kernel_size: int = 5
+    time_channels: int = 64
+    time_cond_in_channels: int = 12
+    time_cond_channels: int = 64
+    cond_channels: int = 6
+    n_attn_layers: int = 0
+    use_res_last: bool = False
+
+
+@dataclass
 class ModelConfig:
     name: str
     denoiser: DenoiserConfig
@@ -129,6 +146,6 @@ def small_autoencoder() -> AutoEncoderConfig:
 
 
 __all__ = [
-    "DenoiserConfig", "AutoEncoderConfig", "Encoder1DConfig", "EcapaConfig", "ModelConfig",
+    "DenoiserConfig", "AutoEncoderConfig", "Encoder1DConfig", "EcapaConfig", "ModelConfig", "UNetConfig",
     "tiny", "base", "midi", "get_config", "base_autoencoder", "small_autoencoder", "asdict"
 ]

@@ -78,6 +78,81 @@ def denoiser_state_dict(cfg: DenoiserConfig, seed: int = 0) -> StateDict:
     return sd
 
 
+# ----------------------------------------------------------------------------- UNET1D (oracle-only so far)
+def unet_state_dict(cfg, seed: int = 0) -> StateDict:
+    """Synthetic ``UNET1D.state_dict()`` in the reference key layout (unet1d.py:30-118, 122-253, 255-375)."""
+    r = _Rng(seed)
+    sd: StateDict = {}
+    k = cfg.kernel_size
+    n = len(cfg.channels)
+    ratios = [1] + list(cfg.ratios)
+    tcc, tci = cfg.time_cond_channels, cfg.time_cond_in_channels
+    out_size = cfg.in_size if cfg.out_size is None else cfg.out_size
+
+    def conv(prefix, co, ci, ks):
+        bound = 1.0 / math.sqrt(ci * ks)
+        sd[prefix + ".weight"] = r.uniform((co, ci, ks), -bound, bound)
+        sd[prefix + ".bias"] = r.uniform((co, ), -bound, bound)
+
+    def lin(prefix, o, i):
+        w, b = r.linear(o, i)
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = w, b
+
+    def gn(prefix, c):
+        sd[prefix + ".weight"] = r.normal((c, ), 1.0, 0.1)
+        sd[prefix + ".bias"] = r.normal((c, ), 0.0, 0.1)
+
+    def conv_block(prefix, in_c, out_c, skip_c):
+        cin = in_c + skip_c + tcc
+        conv(prefix + ".conv1", out_c, cin, k)
+        gn(prefix + ".gn1", cin)
+        conv(prefix + ".conv2", out_c, out_c, k)
+        gn(prefix + ".gn2", out_c)
+        lin(prefix + ".time_mlp.0", 128, cfg.time_channels)
+        lin(prefix + ".time_mlp.2", 2 * out_c, 128)
+        if cfg.cond_channels > 0:
+            lin(prefix + ".cond_mlp.0", 128, cfg.cond_channels)
+            lin(prefix + ".cond_mlp.2", 2 * out_c, 128)
+        if skip_c:
+            conv(prefix + ".to_out", out_c, in_c, 1)
+
+    def attn(prefix, c):
+        gn(prefix + ".norm", c)
+        conv(prefix + ".qkv_proj", 3 * c, c, 1)
+        conv(prefix + ".out_proj", c, c, 1)
+
+    if tcc:
+        conv("cond_emb_time.0.0", tcc, tci, k)
+        for i in range(n):
+            conv(f"cond_emb_time.{i + 1}.0", tcc, tcc, k)
+    in0 = cfg.in_size + (tci if not tcc else 0)
+    ins = [in0] + list(cfg.channels[:-1])
+    for i in range(n):
+        p = f"down_layers.{i}"
+        conv_block(p + ".conv", ins[i], ins[i], 0)
+        if i >= 1 and i >= n - cfg.n_attn_layers:
+            attn(p + ".self_attn", ins[i])
+        conv(p + ".pool", cfg.channels[i], ins[i], k)
+    conv_block("middle_block.conv", cfg.channels[-1], cfg.channels[-1], 0)
+    if cfg.n_attn_layers > 0:
+        attn("middle_block.self_attn", cfg.channels[-1])
+    for i in range(1, n + 1):
+        p = f"up_layers.{i - 1}"
+        last = i == n
+        ic = cfg.channels[n - i]
+        oc = out_size if last else cfg.channels[n - i - 1]
+        ratio = ratios[n - i]
+        if ratio == 1:
+            if ic != oc:
+                conv(p + ".up", oc, ic, 3)
+        else:
+            conv(p + ".up.1", oc, ic, 3)
+        conv_block(p + ".conv", oc, oc, in0 if last else oc)
+        if not last and i <= cfg.n_attn_layers:
+            attn(p + ".self_attn", oc)
+    return sd
+
+
 # ----------------------------------------------------------------------------- PQMF design
 def _kaiser_lowpass(wc: float, atten: float, n_taps=None):
     from scipy.signal import firwin, kaiserord

@@ -444,3 +444,108 @@ def ecapa_forward(sd: StateDict, cfg, z: Tensor) -> Tensor:
     v = _bn_eval(sd, "asp_bn", torch.cat([mean, std], dim=1).unsqueeze(2))
     out = _reflect_conv(sd, "fc.conv", v).squeeze(2)
     return torch.tanh(out) if cfg.use_tanh else out
+
+
+# =============================================================================
+# UNET1D conv denoiser (after/diffusion/networks/unet1d.py, blocks.py) -- SURVEY.md section 8f rank 3.
+# No shipped config binds it and no CUDA path exists yet; the oracle is pinned so that one can be built against it.
+# =============================================================================
+def _spe(t: Tensor, dim: int, max_positions: float = 10000.0, scale: float = 32.0) -> Tensor:
+    """[sin(w x), cos(w x)], x = scale * t, w_f = max_positions^(-2 f / dim); unet1d.py:7-25."""
+    x = t.reshape(-1) * scale
+    f = torch.arange(dim // 2, dtype=torch.float32)
+    w = ((1.0 / max_positions)**(2 * f / dim)).to(x.dtype)
+    a = x[:, None] * w[None, :]
+    return torch.cat([a.sin(), a.cos()], dim=-1)
+
+
+def _same_conv(sd, prefix, x, stride=1):
+    """nn.Conv1d with padding='same' (stride 1) or padding = k // 2 (strided); unet1d.py:46-50, 149-158."""
+    w = sd[prefix + ".weight"]
+    return F.conv1d(x, w, sd[prefix + ".bias"], stride=stride, padding=w.shape[-1] // 2)
+
+
+def _unet_conv_block(sd, prefix, x, time_emb, cond, skip=None, time_cond=None, res=True):
+    """GN -> SiLU -> conv -> (x * t_mult + t_add) -> (x * c_mult + c_add) -> GN -> SiLU -> conv (+ to_out(x_in));
+    unet1d.py:84-118.  The residual branch sees the input BEFORE skip / time_cond are concatenated."""
+    x_in = x
+    parts = [x] + ([skip] if skip is not None else []) + ([time_cond] if time_cond is not None else [])
+    h = torch.cat(parts, dim=1)
+    C = h.shape[1]
+    h = F.silu(F.group_norm(h, min(16, C // 4), sd[prefix + ".gn1.weight"], sd[prefix + ".gn1.bias"]))
+    h = _same_conv(sd, prefix + ".conv1", h)
+    t = F.linear(F.silu(F.linear(time_emb, sd[prefix + ".time_mlp.0.weight"], sd[prefix + ".time_mlp.0.bias"])),
+                 sd[prefix + ".time_mlp.2.weight"], sd[prefix + ".time_mlp.2.bias"])
+    t_mult, t_add = t.chunk(2, dim=1)
+    h = h * t_mult[:, :, None] + t_add[:, :, None]
+    if (prefix + ".cond_mlp.0.weight") in sd:
+        c = F.linear(F.silu(F.linear(cond, sd[prefix + ".cond_mlp.0.weight"], sd[prefix + ".cond_mlp.0.bias"])),
+                     sd[prefix + ".cond_mlp.2.weight"], sd[prefix + ".cond_mlp.2.bias"])
+        c_mult, c_add = c.chunk(2, dim=1)
+        h = h * c_mult[:, :, None] + c_add[:, :, None]
+    Co = h.shape[1]
+    h = F.silu(F.group_norm(h, min(16, Co // 4), sd[prefix + ".gn2.weight"], sd[prefix + ".gn2.bias"]))
+    h = _same_conv(sd, prefix + ".conv2", h)
+    if not res:
+        return h
+    if (prefix + ".to_out.weight") in sd:
+        x_in = _same_conv(sd, prefix + ".to_out", x_in)
+    return h + x_in
+
+
+def _self_attention_1d(sd, prefix, x, n_head):
+    """GroupNorm(1) -> 1x1 qkv -> full softmax attention per head (scale d^-1/4 on q and k) -> 1x1 out + residual;
+    blocks.py:201-243."""
+    n, c, s = x.shape
+    y = F.group_norm(x, 1, sd[prefix + ".norm.weight"], sd[prefix + ".norm.bias"])
+    qkv = F.conv1d(y, sd[prefix + ".qkv_proj.weight"], sd[prefix + ".qkv_proj.bias"])
+    qkv = qkv.reshape(n, n_head * 3, c // n_head, s).transpose(2, 3)
+    q, k, v = qkv.chunk(3, dim=1)
+    scale = k.shape[3]**-0.25
+    att = torch.softmax((q * scale) @ (k.transpose(2, 3) * scale), dim=3)
+    y = (att @ v).transpose(2, 3).reshape(n, c, s)
+    return x + F.conv1d(y, sd[prefix + ".out_proj.weight"], sd[prefix + ".out_proj.bias"])
+
+
+def unet1d_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Optional[Tensor], time_cond: Optional[Tensor]) -> Tensor:
+    """``UNET1D.forward``; unet1d.py:376-429 (both the per-scale time_cond embedding path and the concat path).
+    x (N, in_size, T), time (N,), cond (N, cond_channels), time_cond (N, time_cond_in_channels, T) -> (N, out_size, T)."""
+    sd = _cast(sd, x.dtype)
+    n = len(cfg.channels)
+    ratios = [1] + list(cfg.ratios)
+    temb = _spe(time.to(x.dtype), cfg.time_channels)
+    skips, tcs = [], []
+    tc = time_cond
+    if not cfg.time_cond_channels:
+        if cfg.time_cond_in_channels:
+            x = torch.cat([x, time_cond], dim=1)
+        tc = None
+    for i in range(n):
+        if cfg.time_cond_channels:
+            tc = F.silu(_same_conv(sd, f"cond_emb_time.{i}.0", tc, stride=1 if i == 0 else ratios[i - 1]))
+        p = f"down_layers.{i}"
+        skip = _unet_conv_block(sd, p + ".conv", x, temb, cond, time_cond=tc)
+        if (p + ".self_attn.norm.weight") in sd:
+            skip = _self_attention_1d(sd, p + ".self_attn", skip, 4)
+        x = _same_conv(sd, p + ".pool", skip, stride=ratios[i])
+        skips.append(skip)
+        tcs.append(tc)
+    if cfg.time_cond_channels:
+        tc = F.silu(_same_conv(sd, f"cond_emb_time.{n}.0", tc, stride=ratios[n - 1]))
+    x = _unet_conv_block(sd, "middle_block.conv", x, temb, cond, time_cond=tc)
+    if "middle_block.self_attn.norm.weight" in sd:
+        x = _self_attention_1d(sd, "middle_block.self_attn", x, cfg.channels[-1] // 32)
+    for i in range(1, n + 1):
+        p = f"up_layers.{i - 1}"
+        skip, tc_i = skips.pop(), tcs.pop()
+        ratio = ratios[n - i]
+        if ratio != 1:
+            x = F.interpolate(x, scale_factor=ratio, mode="nearest")
+            x = _same_conv(sd, p + ".up.1", x)
+        elif (p + ".up.weight") in sd:
+            x = _same_conv(sd, p + ".up", x)
+        x = _unet_conv_block(sd, p + ".conv", x, temb, cond, skip=skip, time_cond=tc_i,
+                             res=(cfg.use_res_last if i == n else True))
+        if (p + ".self_attn.norm.weight") in sd:
+            x = _self_attention_1d(sd, p + ".self_attn", x, 4)
+    return x

@@ -144,3 +144,25 @@ def test_stream_sample_matches_reference(golden, name):
         out = O.sample_stream(sd, cfg, cache, T(g["x0"][b]), T(g["cond"][b]), T(g["time_cond"][b]), int(g["nb_steps"]),
                               float(g["guidance_timbre"]), float(g["guidance_structure"]))
         assert rel(out, g["out"][b]) < 2e-5, (b, rel(out, g["out"][b]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UNET1D conv denoiser: oracle only so far, fixtures from tests/golden/make_golden_unet.py
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["attn", "concat"])
+def test_unet1d_matches_reference(golden, tag):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from unet_cases import CASES
+    cfg, wseed = CASES[tag]
+    g = golden(f"unet_{tag}")
+    assert int(g["weight_seed"]) == wseed
+    sd = synth.unet_state_dict(cfg, wseed)
+    cond = T(g["cond"]) if cfg.cond_channels else None
+    out = O.unet1d_forward(sd, cfg, T(g["x"]), T(g["time"]), cond, T(g["time_cond"]))
+    assert out.shape == g["out"].shape
+    assert rel(out, g["out"]) < 1e-5, rel(out, g["out"])
+    out64 = O.unet1d_forward(sd, cfg, T(g["x"]).double(), T(g["time"]).double(), cond.double() if cond is not None else None,
+                             T(g["time_cond"]).double())
+    assert rel(g["out"], out64) < 2e-5
