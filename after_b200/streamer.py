@@ -153,3 +153,101 @@ class Streamer:
         raise NotImplementedError("latent-map MLP (after/diffusion/latent_plot.py) is an export-time UI artefact: out of scope")
 
     map2latent = latent2map
+
+
+class MidiStreamer:
+    """The MIDI variant of the exported model (``after_scripts/export_midi.py:150-450``): the structure condition is a
+    piano roll rasterised from ``n_poly`` (pitch, velocity) signal pairs instead of an encoded audio stream, the CFG rows
+    are (cond, roll) / (cond, drop) / (drop, drop) with ``f = g_structure / max(g_timbre, 0.1)`` (:322-360), and ``timbre``
+    repeats the embedding over the encoded frames (:383-398).  Methods: ``timbre`` (1 -> zt), ``diffuse`` /
+    ``generate`` (2 n_poly + zt -> latents / audio), ``decode``.  Same semantics notes as ``Streamer``."""
+
+    def __init__(self, engine: Engine, n_poly: int = 4, n_signal_timbre: int = 64, chunk_size: int = 4, latent_range: float = 1.0):
+        if not (engine.has_denoiser and engine.has_codec and engine.has_timbre):
+            raise RuntimeError("MidiStreamer needs denoiser, autoencoder and timbre-encoder weights")
+        if engine.cfg.tcond_dim != 128:
+            raise RuntimeError("MidiStreamer needs a midi model (structure condition = 128-pitch piano roll)")
+        self.engine = engine
+        self.n_poly = n_poly
+        self.chunk_size = chunk_size
+        self.n_signal_timbre = n_signal_timbre
+        self.latent_range = latent_range
+        self.zt_channels = engine.cfg.cond_dim
+        self.ae_latents = engine.cfg.n_channels
+        self.ae_ratio = engine.ae_ratio
+        self.drop_value = engine.cfg.drop_value
+        self.sr = 44100
+        self.zt_buffer = n_signal_timbre * self.ae_ratio
+        self.nb_steps = (1, )
+        self.guidance_timbre = (1.0, )
+        self.guidance_structure = (1.0, )
+        self.previous_timbre = torch.zeros(4, self.ae_latents, n_signal_timbre, device=engine.device)
+        self.last_zsem = torch.zeros(4, self.zt_channels, device=engine.device)  # export_midi.py:193
+        r = self.ae_ratio
+        cin = 2 * n_poly + self.zt_channels
+        self.methods = {
+            "timbre": (1, 1, self.zt_channels, r),
+            "generate": (cin, r, 1, 1),
+            "diffuse": (cin, r, self.ae_latents, r),
+            "decode": (self.ae_latents, r, 1, 1),
+        }
+
+    get_guidance_timbre = Streamer.get_guidance_timbre
+    set_guidance_timbre = Streamer.set_guidance_timbre
+    get_guidance_structure = Streamer.get_guidance_structure
+    set_guidance_structure = Streamer.set_guidance_structure
+    get_nb_steps = Streamer.get_nb_steps
+    set_nb_steps = Streamer.set_nb_steps
+    _check = Streamer._check
+
+    def sample(self, x_last, cond, time_cond):
+        """export_midi.py:362-381 (per-step KV caches when the engine streams)."""
+        fn = self.engine.sample_stream if self.engine.streaming else self.engine.sample
+        return fn(x_last, cond, time_cond, self.nb_steps[0], self.guidance_timbre[0], self.guidance_structure[0],
+                  cfg_variant=L.CFG_MIDI, clamp=0.1)
+
+    def timbre(self, x):
+        x = self._check("timbre", x)
+        z = self.engine.ae_encode(x)
+        n, t = z.shape[0], z.shape[-1]
+        self.previous_timbre[:n] = torch.cat((self.previous_timbre[:n], z), -1)[..., t:]
+        zsem = self.engine.timbre_encode(self.previous_timbre[:n].contiguous())
+        return zsem.unsqueeze(-1).repeat(1, 1, t) / self.latent_range
+
+    def piano_roll(self, notes: torch.Tensor) -> torch.Tensor:
+        """(1, 2 n_poly, T) pitch / velocity signals -> (1, 128, T) roll, exactly as export_midi.py:408-415 fills it:
+        voices in order (later voices overwrite), a frame is written when ITS velocity is > 0, the value is velocity / 128,
+        and -- the reference indexes with the voice's whole pitch row, ``notes[:, 2 i].long()`` -- it is written at every
+        pitch that voice takes anywhere in the buffer (one pitch for a held note)."""
+        T = notes.shape[-1]
+        roll = torch.zeros(1, 128, T, device=notes.device, dtype=torch.float32)
+        for i in range(self.n_poly):
+            pitch = notes[0, 2 * i].long()
+            vel = notes[0, 2 * i + 1]
+            on = vel > 0
+            if bool(on.any()):
+                rows = torch.unique(pitch)
+                roll[0, rows[:, None], torch.nonzero(on)[:, 0][None, :]] = (vel[on] / 128)[None, :]
+        return roll
+
+    def diffuse(self, x, noise: Optional[torch.Tensor] = None):
+        x = self._check("diffuse", x)
+        n, T = x.shape[0], x.shape[-1]
+        zsem = x[:, -self.zt_channels:].mean(-1) * self.latent_range
+        time_cond = self.piano_roll(x[:1, :2 * self.n_poly])
+        if noise is None:
+            noise = torch.randn(n, self.ae_latents, T)
+        noise = noise.to(self.engine.device, torch.float32)
+        out = self.sample(noise[:1].contiguous(), zsem[:1].contiguous(), time_cond.contiguous())
+        return out.repeat(n, 1, 1) if n > 1 else out
+
+    def decode(self, x):
+        return self.engine.ae_decode(self._check("decode", x))
+
+    def generate(self, x, noise: Optional[torch.Tensor] = None):
+        return self.decode(self.diffuse(x, noise))
+
+    def latent2map(self, x):
+        raise NotImplementedError("latent-map MLP (after/diffusion/latent_plot.py) is an export-time UI artefact: out of scope")
+
+    map2latent = latent2map
