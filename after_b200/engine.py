@@ -183,6 +183,13 @@ class Engine:
         except Exception:
             pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def _dev(self, t: torch.Tensor, name: str) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
             raise TypeError(f"{name} must be a torch.Tensor")

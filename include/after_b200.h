@@ -217,8 +217,8 @@ int after_generate_host(after_handle h, const float* audio_structure, const floa
                         float* audio_out, int B, int64_t samples, int nb_steps, float guidance_timbre,
                         float guidance_structure, void* stream);
 
-/* Introspection for benchmarks: kernels launched by this handle since creation, bytes of device
- * memory held, codec ratio (samples per latent frame). */
+/* Introspection for benchmarks: kernels launched by the library in this process (all handles; graph replays count
+ * their captured kernels), bytes of device memory held by this handle, codec ratio (samples per latent frame). */
 int64_t after_launch_count(after_handle h);
 int64_t after_device_bytes(after_handle h);
 int after_ae_ratio(after_handle h);
