@@ -57,6 +57,9 @@ class Encoder1D:
     def forward(self, z):
         return self.engine.structure_encode(z)
 
+    # same arithmetic in the reference (encoder.py:300-322); its cached-conv state across calls is not carried here
+    forward_stream = forward
+
     def eval(self):
         return self
 
