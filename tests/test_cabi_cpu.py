@@ -68,3 +68,21 @@ def test_no_gpu_means_loud_failure(lib):
     from after_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine()
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    """examples/c_host.c: a C program binds the ABI with nothing but the header; without a CUDA device it must stop at
+    after_create with the library's message (exit code 2), with one it samples (exit code 0)."""
+    import subprocess
+    libdir = os.path.join(ROOT, "after_b200", "lib")
+    exe = tmp_path / "c_host"
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_host.c"),
+                           "-o", str(exe), "-L", libdir, "-lafter_b200", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "sample ok" in r.stdout and "yes" in r.stdout
+    else:
+        assert r.returncode == 2, r.stdout + r.stderr
+        assert "after_create failed" in r.stdout and ("no CPU fallback" in r.stdout or "CUDA" in r.stdout)
