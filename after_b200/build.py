@@ -1,6 +1,6 @@
 """Build libafter_b200.so (sm_100a only) in-tree with nvcc.
 
-    python -m after_b200.build [--force]
+    python -m after_b200.build [--force] [--debug]
 
 The library lands in ``after_b200/lib/`` (git-ignored, shipped to the GPU box by gpurun).
 There is a single translation unit (``csrc/api.cu``) on purpose: the whole build is one nvcc
@@ -30,32 +30,35 @@ def _sources():
     return files
 
 
-def _digest():
+def _digest(debug: bool = False):
     h = hashlib.sha256()
     for f in _sources():
         h.update(f.encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + (["-DAFTER_DEBUG"] if debug else [])).encode())
     return h.hexdigest()
 
 
-def is_fresh() -> bool:
+def is_fresh(debug: bool = False) -> bool:
     if not (os.path.exists(LIB) and os.path.exists(STAMP)):
         return False
     with open(STAMP) as fh:
-        return fh.read().strip() == _digest()
+        return fh.read().strip() == _digest(debug)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if sources changed; returns its path."""
-    if not force and is_fresh():
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile the library if sources changed; returns its path.  ``debug`` adds -DAFTER_DEBUG: the A/B environment
+    knobs (AFTER_ATTN, AFTER_PDL, AFTER_NO_GRAPH, AFTER_MLP_KSPLIT, ...) and the in-kernel %globaltimer traces exist
+    only in that build; the release library ignores the environment."""
+    debug = debug or os.environ.get("AFTER_B200_DEBUG_BUILD") == "1"
+    if not force and is_fresh(debug):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libafter_b200.so")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    cmd = [nvcc] + NVCC_FLAGS + (["-DAFTER_DEBUG"] if debug else []) + (["-Xptxas", "-v"] if verbose else []) + [
         os.path.join(CSRC, "api.cu"), "-o", LIB, "-lcuda"
     ]
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,10 +67,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(proc.stderr)
     with open(STAMP, "w") as fh:
-        fh.write(_digest())
+        fh.write(_digest(debug))
     return LIB
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv)
     print(path)

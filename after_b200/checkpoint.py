@@ -86,7 +86,22 @@ def parse_gin(text: str, macros: Optional[Dict[str, Any]] = None) -> Tuple[Dict[
     macros = {}
     bindings: Bindings = {}
     block: Optional[Tuple[str, str]] = None
-    lines = text.splitlines()
+    # gin.operative_config_str() wraps every binding longer than 80 columns as ``selector = \`` + the value indented on
+    # the next line(s) (after/diffusion/model.py:264-265 writes config.gin that way): join backslash continuations first.
+    # The joined line keeps the indentation of its FIRST physical line, which is what decides block membership below.
+    lines = []
+    pending = None
+    for raw in text.splitlines():
+        body = _strip_comment(raw)
+        if pending is not None:
+            body = pending + " " + body.strip()
+            pending = None
+        if body.rstrip().endswith("\\"):
+            pending = body.rstrip()[:-1].rstrip()
+            continue
+        lines.append(body)
+    if pending is not None:
+        lines.append(pending)
     i = 0
     while i < len(lines):
         raw = lines[i]
@@ -153,8 +168,11 @@ def model_config_from_gin(text: str, in_size: Optional[int] = None, n_signal: Op
     d = _find(b, "DenoiserV2")
     if not d:
         raise ValueError("config binds no DenoiserV2 (the v1 Denoiser / UNET1D nets are out of scope)")
-    if d.get("pos_emb_type", "rotary") != "rotary" or not d.get("causal", True):
-        raise ValueError("only the causal, rotary DenoiserV2 of the shipped configs is supported")
+    # reference defaults (transformerv2.py:463-476) are pos_emb_type='learnable', causal=False: a config that does not bind
+    # them asks for a model this path does not implement, so it is rejected rather than silently run as rotary/causal
+    if d.get("pos_emb_type", "learnable") != "rotary" or not d.get("causal", False):
+        raise ValueError("only the causal, rotary DenoiserV2 of the shipped configs is supported "
+                         "(config must bind DenoiserV2.pos_emb_type = 'rotary' and DenoiserV2.causal = True)")
     base = DenoiserConfig()
 
     def pick(key, default):

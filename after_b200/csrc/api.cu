@@ -28,9 +28,7 @@ struct after_ctx {
   StructureEncoder structure;
   TimbreEncoder timbre;
   bool have_codec = false, have_structure = false, have_timbre = false;
-  // pinned staging for the *_host entry points
-  float* pin = nullptr;
-  size_t pin_floats = 0;
+  // device staging of the *_host entry points (the copies go straight from / to the caller's host pointers)
   float* dev_io = nullptr;
   size_t dev_io_floats = 0;
   float* chain = nullptr;  // z_s | z_t | time_cond | cond | x scratch of after_generate
@@ -74,17 +72,25 @@ int guarded(after_handle h, F&& f) {
   }
 }
 
+// Orders the library's work stream after the caller's stream on entry and the caller's stream after the work stream on
+// EVERY exit path, exceptions included (work enqueued before a failure must still be ordered before whatever the
+// caller enqueues next: outputs are allocated on the caller's stream).  All argument validation happens before it.
+struct BridgeScope {
+  StreamBridge& b;
+  cudaStream_t user;
+  BridgeScope(StreamBridge& bridge, void* stream) : b(bridge), user(reinterpret_cast<cudaStream_t>(stream)) { b.enter(user); }
+  ~BridgeScope() {
+    if (cudaEventRecord(b.e_out, b.work) == cudaSuccess) cudaStreamWaitEvent(user, b.e_out, 0);
+  }
+  BridgeScope(const BridgeScope&) = delete;
+  BridgeScope& operator=(const BridgeScope&) = delete;
+};
+
 void require_ready(after_handle h) {
   AFTER_REQUIRE(h->precision >= 0, AFTER_ESTATE, "after_finalize_weights has not been called on this handle");
 }
 
 void ensure_staging(after_handle h, size_t floats) {
-  if (floats > h->pin_floats) {
-    if (h->pin) cudaFreeHost(h->pin);
-    h->pin = nullptr;
-    AFTER_CUDA_CHECK(cudaMallocHost(&h->pin, floats * sizeof(float)));
-    h->pin_floats = floats;
-  }
   if (floats > h->dev_io_floats) {
     if (h->dev_io) cudaFree(h->dev_io);
     h->dev_io = nullptr;
@@ -153,7 +159,6 @@ int after_destroy(after_handle h) {
     h->codec.destroy();
     h->bridge.destroy();
     h->arena.release();
-    if (h->pin) cudaFreeHost(h->pin);
     if (h->dev_io) cudaFree(h->dev_io);
     if (h->chain) cudaFree(h->chain);
   }
@@ -233,10 +238,8 @@ int after_denoiser_forward(after_handle h, const float* x, const float* time, co
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.forward(x, time, cond, time_cond, out, N, T, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -247,11 +250,9 @@ int after_model_forward(after_handle h, const float* x, const float* time, const
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.model_forward(x, time, cond, time_cond, out, B, T, guidance_timbre, guidance_structure, cfg_variant, clamp,
                               h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -262,11 +263,9 @@ int after_sample(after_handle h, const float* x0, const float* cond, const float
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x0 && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.sample(x0, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
                        h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -277,10 +276,8 @@ int after_denoiser_forward_cached(after_handle h, const float* x, const float* t
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
     h->denoiser.check_cache_index(cache_index);
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.forward(x, time, cond, time_cond, out, N, T, h->bridge.work, cache_index);
-    h->bridge.exit(user);
   });
 }
 
@@ -292,11 +289,9 @@ int after_model_forward_cached(after_handle h, const float* x, const float* time
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
     h->denoiser.check_cache_index(cache_index);
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.model_forward(x, time, cond, time_cond, out, B, T, guidance_timbre, guidance_structure, cfg_variant, clamp,
                               h->bridge.work, cache_index);
-    h->bridge.exit(user);
   });
 }
 
@@ -304,10 +299,8 @@ int after_roll_cache(after_handle h, int roll_size, int cache_index, void* strea
   return guarded(h, [&] {
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.roll_cache(roll_size, cache_index, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -315,10 +308,8 @@ int after_reset_cache(after_handle h, void* stream) {
   return guarded(h, [&] {
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.reset_cache(h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -329,11 +320,9 @@ int after_sample_stream(after_handle h, const float* x_last, const float* cond, 
     require_ready(h);
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x_last && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->denoiser.sample(x_last, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
                        h->bridge.work, /*stream=*/true);
-    h->bridge.exit(user);
   });
 }
 
@@ -353,15 +342,13 @@ int after_sample_host(after_handle h, const float* x0, const float* cond, const 
     float* dt = dc + nc;
     float* dout = dt + nt;
     cudaStream_t st = h->bridge.work;
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     AFTER_CUDA_CHECK(cudaMemcpyAsync(dx, x0, nx * 4, cudaMemcpyHostToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(dc, cond, nc * 4, cudaMemcpyHostToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(dt, time_cond, nt * 4, cudaMemcpyHostToDevice, st));
     h->denoiser.sample(dx, dc, dt, dout, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp, st);
     AFTER_CUDA_CHECK(cudaMemcpyAsync(out, dout, nx * 4, cudaMemcpyDeviceToHost, st));
     AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
-    h->bridge.exit(user);
   });
 }
 
@@ -370,10 +357,8 @@ int after_ae_encode(after_handle h, const float* audio, float* z, int B, int64_t
     require_ready(h);
     AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
     AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->codec.encode(audio, z, B, samples, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -382,10 +367,8 @@ int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, 
     require_ready(h);
     AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
     AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->codec.decode(z, audio, B, T, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -394,10 +377,8 @@ int after_structure_encode(after_handle h, const float* z, float* time_cond, int
     require_ready(h);
     AFTER_REQUIRE(h->have_structure, AFTER_ESTATE, "no structure-encoder weights on this handle");
     AFTER_REQUIRE(z && time_cond, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->structure.forward(z, time_cond, B, T, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -406,10 +387,8 @@ int after_timbre_encode(after_handle h, const float* z, float* cond, int B, int 
     require_ready(h);
     AFTER_REQUIRE(h->have_timbre, AFTER_ESTATE, "no timbre-encoder weights on this handle");
     AFTER_REQUIRE(z && cond, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     h->timbre.forward(z, cond, B, T, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -449,11 +428,9 @@ int after_generate(after_handle h, const float* audio_structure, const float* au
   return guarded(h, [&] {
     require_ready(h);
     AFTER_REQUIRE(audio_structure && audio_timbre && x0 && audio_out, AFTER_EINVAL, "null tensor pointer");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     generate_device(h, audio_structure, audio_timbre, x0, audio_out, B, samples, nb_steps, guidance_timbre, guidance_structure,
                     h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 
@@ -473,15 +450,13 @@ int after_generate_host(after_handle h, const float* audio_structure, const floa
     float* d_o = d_t + na;
     float* d_x = d_o + na;
     cudaStream_t st = h->bridge.work;
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     AFTER_CUDA_CHECK(cudaMemcpyAsync(d_s, audio_structure, na * 4, cudaMemcpyHostToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(d_t, audio_timbre, na * 4, cudaMemcpyHostToDevice, st));
     AFTER_CUDA_CHECK(cudaMemcpyAsync(d_x, x0, nx * 4, cudaMemcpyHostToDevice, st));
     generate_device(h, d_s, d_t, d_x, d_o, B, samples, nb_steps, guidance_timbre, guidance_structure, st);
     AFTER_CUDA_CHECK(cudaMemcpyAsync(audio_out, d_o, na * 4, cudaMemcpyDeviceToHost, st));
     AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
-    h->bridge.exit(user);
   });
 }
 
@@ -518,10 +493,8 @@ int after_debug_gemm(after_handle h, const float* A, const float* W, const float
   return guarded(h, [&] {
     AFTER_REQUIRE(A && W && C, AFTER_EINVAL, "null tensor pointer");
     AFTER_REQUIRE(M >= 1 && N >= 1 && K >= 1, AFTER_EINVAL, "bad GEMM shape");
-    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    h->bridge.enter(user);
+    BridgeScope bridge(h->bridge, stream);
     debug_gemm(A, W, bias, C, M, N, K, precision, h->bridge.work);
-    h->bridge.exit(user);
   });
 }
 

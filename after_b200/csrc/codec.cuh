@@ -31,7 +31,7 @@ struct GraphCache {
   std::map<std::vector<int>, Entry> graphs;
   bool enabled = true;
   void init() {
-    const char* ng = getenv("AFTER_NO_GRAPH");
+    const char* ng = debug_env("AFTER_NO_GRAPH");
     enabled = !(ng && ng[0] == '1');
   }
   template <typename F>

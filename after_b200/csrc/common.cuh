@@ -27,6 +27,17 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::after::Error((code), std::string(msg));                                \
   } while (0)
 
+// A/B and trace knobs (AFTER_* environment variables, GemmEpi::debug_skip / debug_ts, the fused-MLP %globaltimer trace)
+// exist only in builds compiled with -DAFTER_DEBUG (python -m after_b200.build --debug): the release library never reads
+// the environment, and the kernels' debug branches are compiled out (kDebugBuild is a compile-time false).
+#ifdef AFTER_DEBUG
+constexpr bool kDebugBuild = true;
+inline const char* debug_env(const char* name) { return getenv(name); }
+#else
+constexpr bool kDebugBuild = false;
+inline const char* debug_env(const char*) { return nullptr; }
+#endif
+
 #define AFTER_STR_(x) #x
 #define AFTER_STR(x) AFTER_STR_(x)
 
@@ -36,11 +47,11 @@ struct Error : std::runtime_error {
 // scheduled once every CTA of this one has got this far), and are launched through launch_k() with the
 // programmatic-stream-serialization attribute: the next kernel's launch latency, block scheduling and on-chip set-up
 // overlap the tail of this one.  Only kernels that call pdl_wait() before touching global memory may be launched this
-// way.  AFTER_PDL=0 turns the attribute off (plain stream order) for A/B measurements.
+// way.  AFTER_PDL=0 (debug builds only) turns the attribute off (plain stream order) for A/B measurements.
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AFTER_PDL");
+    const char* e = debug_env("AFTER_PDL");
     v = (e && e[0] == '0') ? 0 : 1;  // on by default: +2.4 % steps/s at base B=8 (profiles/r01b_ab_knobs.jsonl)
   }
   return v == 1;

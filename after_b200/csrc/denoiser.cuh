@@ -184,23 +184,18 @@ struct Denoiser {
     guidance = arena->alloc<float>(4);
     flag_stride = maxN * ceil_div(maxT, 2 * tc::BM);
     mlp_flags = arena->alloc<int>((size_t)L * flag_stride);
-    {  // opt-in dynamic shared memory of the bulk-copy attention kernel (must not first happen inside a stream capture)
+#ifdef AFTER_DEBUG
+    {  // opt-in dynamic shared memory of the staged A/B variant (must not first happen inside a stream capture)
       auto set = [](const void* f, size_t bytes) {
         AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
       };
-      auto bytes = [](int nh, int maxk) { return 128 + (size_t)(4 + 2 * maxk) * nh * 64 * sizeof(float); };
-      set((const void*)attn_chunk4_bulk_kernel<8, 12>, bytes(8, 12));
-      set((const void*)attn_chunk4_bulk_kernel<8, 20>, bytes(8, 20));
-      set((const void*)attn_chunk4_bulk_kernel<8, 32>, bytes(8, 32));
-      set((const void*)attn_chunk4_bulk_kernel<4, 12>, bytes(4, 12));
-      set((const void*)attn_chunk4_bulk_kernel<4, 20>, bytes(4, 20));
-      set((const void*)attn_chunk4_bulk_kernel<4, 32>, bytes(4, 32));
       auto wbytes = [](int nh, int maxk) { return 128 + (size_t)(16 + maxk) * 2 * nh * 64 * sizeof(float); };
       set((const void*)attn_warp_chunk_kernel<8, 12, true, 4>, wbytes(8, 12));
       set((const void*)attn_warp_chunk_kernel<8, 20, true, 4>, wbytes(8, 20));
       set((const void*)attn_warp_chunk_kernel<4, 12, true, 4>, wbytes(4, 12));
       set((const void*)attn_warp_chunk_kernel<4, 20, true, 4>, wbytes(4, 20));
     }
+#endif
     cacheW = c.max_cache_size;
     AFTER_REQUIRE(cacheW >= 0 && cacheW <= 64, AFTER_EINVAL, "max_cache_size must be in [0, 64]");
     if (cacheW > 0) {
@@ -215,7 +210,7 @@ struct Denoiser {
       AFTER_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<SKINNY_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float))));
     }
-    const char* ng = getenv("AFTER_NO_GRAPH");
+    const char* ng = debug_env("AFTER_NO_GRAPH");
     use_graph = !(ng && ng[0] == '1');
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
   }
@@ -294,45 +289,35 @@ struct Denoiser {
     // q,k,v read once + h read/write + operand write; ~2 * keys * 64 * 2 flops per (token, head)
     ProfScope prof(KC_ATTENTION, st, (double)rows * H * 64.0 * 4.0 * (cfg.attention_chunk_size + cfg.local_attention_size - 1),
                    (double)rows * D * (12.0 + 8.0 + (tc_mode() ? 2.0 * (nprod() > 1 ? 2 : 1) : 4.0)));
-    // AFTER_ATTN = warp (default) | staged | block | bulk  (A/B runs; measured at base B=8 fp32: 1354 / 1309 / 1314 / 1287
-    // steps/s, profiles/r01b_ab_attn*.jsonl -- staging the key rows in shared memory costs occupancy and a second wave)
-    static int variant = -1;
-    if (variant < 0) {
-      const char* e = getenv("AFTER_ATTN");
-      variant = (e && !strcmp(e, "block")) ? 1 : (e && !strcmp(e, "bulk")) ? 2 : (e && !strcmp(e, "staged")) ? 0 : 3;
-    }
-    const bool warp_ok = cfg.attention_chunk_size == 4 && MAXK <= 20;  // wider bands: sc[4][MAXK] would spill
-    if (warp_ok && variant == 0 && T % 16 == 0) {
-      const int n_seq = rows / T, chunks = n_seq * (T / 4);
-      const size_t smem = 128 + (size_t)(16 + cfg.local_attention_size - 1) * 2 * D * sizeof(float);
-      launch_k(attn_warp_chunk_kernel<NH, MAXK, true, 4>, dim3(chunks / 4), dim3(128), smem, st, qkv, h, o, adaC_step, L * 2 * D,
-               l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
-               mlp_flags + (size_t)l * flag_stride, flag_stride);
-    } else if (warp_ok && (variant == 0 || variant == 3)) {
-      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      static int qpw = -1;  // AFTER_ATTN_QPW = queries per warp (4 | 2 | 1)
-      if (qpw < 0) { const char* e = getenv("AFTER_ATTN_QPW"); qpw = e ? atoi(e) : 4; }
-#define AFTER_LAUNCH_ATTN_WARP(Q)                                                                                       \
-  launch_k(attn_warp_chunk_kernel<NH, MAXK, false, Q>, dim3(ceil_div(chunks * (4 / Q), 4)), dim3(128), 0, st, qkv, h, o, \
-           adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size, \
+    const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
+    bool done = false;
+    if constexpr (MAXK <= 20) {  // wider bands: sc[4][MAXK] would spill -> one-warp-per-token kernel below
+      if (cfg.attention_chunk_size == 4) {
+#define AFTER_LAUNCH_ATTN_WARP(STAGED, Q, GRID, SMEM)                                                                     \
+  launch_k(attn_warp_chunk_kernel<NH, MAXK, STAGED, Q>, dim3(GRID), dim3(128), SMEM, st, qkv, h, o, adaC_step, L * 2 * D,  \
+           l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,                       \
            mlp_flags + (size_t)l * flag_stride, flag_stride)
-      if (qpw == 2) AFTER_LAUNCH_ATTN_WARP(2);
-      else if (qpw == 1) AFTER_LAUNCH_ATTN_WARP(1);
-      else AFTER_LAUNCH_ATTN_WARP(4);
+#ifdef AFTER_DEBUG
+        // A/B variants (debug builds only; base B=8 fp32, profiles/r01b_ab_attn*.jsonl): AFTER_ATTN=staged stages the key
+        // rows in shared memory (-3.4 %), AFTER_ATTN_QPW = 2 | 1 spreads a chunk's queries over 2 / 4 warps (-4 / -7 %)
+        static int staged = -1, qpw = -1;
+        if (staged < 0) { const char* e = debug_env("AFTER_ATTN"); staged = (e && !strcmp(e, "staged")) ? 1 : 0; }
+        if (qpw < 0) { const char* e = debug_env("AFTER_ATTN_QPW"); qpw = e ? atoi(e) : 4; }
+        if (staged && T % 16 == 0) {
+          const size_t smem = 128 + (size_t)(16 + cfg.local_attention_size - 1) * 2 * D * sizeof(float);
+          AFTER_LAUNCH_ATTN_WARP(true, 4, chunks / 4, smem);
+        } else if (qpw == 2) {
+          AFTER_LAUNCH_ATTN_WARP(false, 2, ceil_div(chunks * 2, 4), 0);
+        } else if (qpw == 1) {
+          AFTER_LAUNCH_ATTN_WARP(false, 1, chunks, 0);
+        } else
+#endif
+        AFTER_LAUNCH_ATTN_WARP(false, 4, ceil_div(chunks, 4), 0);
 #undef AFTER_LAUNCH_ATTN_WARP
-    } else if (cfg.attention_chunk_size == 4 && variant == 2) {
-      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
-      const size_t smem = 128 + (size_t)(4 + 2 * mk) * D * sizeof(float);
-      launch_k(attn_chunk4_bulk_kernel<NH, MAXK>, dim3(chunks), dim3(NH * 32), smem, st, qkv, h, o, adaC_step, L * 2 * D,
-               l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
-               mlp_flags + (size_t)l * flag_stride, flag_stride);
-    } else if (cfg.attention_chunk_size == 4) {
-      const int n_seq = rows / T, chunks = n_seq * ((T + 3) / 4);
-      launch_k(attn_chunk4_kernel<NH, MAXK>, dim3(chunks), dim3(NH * 32), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
-               seqmap(), layers[l].n3_g, layers[l].n3_b, n_seq, T, cfg.local_attention_size,
-               mlp_flags + (size_t)l * flag_stride, flag_stride);
-    } else {
+        done = true;
+      }
+    }
+    if (!done) {
       launch_k(attn_adaln_c_ln3_kernel<NH, MAXK>, dim3(ceil_div(rows, 4)), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D,
                l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, rows, T, cfg.attention_chunk_size,
                cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride, flag_stride);

@@ -117,296 +117,9 @@ adaln_t_ln1_kernel(const float* h_in, const float* h_add, float* h_out, RowOpera
 //   (full attention inside the chunk, sliding window of w counted back from the query)
 //   h <- h + softmax(q k^T / sqrt(64)) v ;  h <- LN2(h) * (1 + alpha_c) + beta_c ;  a <- LN3(h) * g3 + b3
 // q/k already carry the rotary embedding (QKV GEMM epilogue).
-// One warp per attention chunk of 4 queries: lane = (query qi = lane >> 3, dsub = lane & 7); per head a lane owns
-// dims [8 dsub, 8 dsub + 8).  The four query groups read the same key/value rows (one coalesced 256-byte request
-// per row and head), dot products are reduced over the 8 lanes of a group with 3 shuffles, and after the head loop
-// each lane holds 8 x NH values of its query's row, so both LayerNorms reduce over 8 lanes only.
-// Requires chunk == 4 (every shipped config; other chunk sizes take the one-warp-per-token kernel below).
+// (Round 1 also carried a block-per-chunk kernel and a cp.async.bulk-staged one; both measured slower --
+// profiles/r01b_ab_attn*.jsonl, profiles/EXPERIMENTS.md -- and were removed from the library.)
 // -------------------------------------------------------------------------------------------
-template <int NH, int MAXK>
-__global__ void __launch_bounds__(NH * 32, 32 / NH)
-attn_chunk4_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
-                   const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
-                   const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
-                   int* zero_flags, int n_zero) {
-  pdl_wait();
-  pdl_trigger();
-  // the fused MLP of this layer (next kernel) counts finished up-projection tiles per row block in zero_flags
-  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
-  // Block = one attention chunk (4 queries), warp = head: NH warps x 1536 chunks keeps ~64 warps resident per SM, which
-  // is what hides the L2 round trips of the key/value rows (the kernel is latency-, not bandwidth-bound).
-  // Phase 1 (all warps): lane = (query qi = lane >> 3, dsub = lane & 7) owns dims [4 dsub, +4) and [32 + 4 dsub, +4) of
-  // this warp's head; scores are reduced over the 8 lanes of a query with 3 shuffles; h + softmax.V goes to smem.
-  // Phase 2 (warps 0..3): one query row each: LayerNorm -> AdaLN-c -> h ; LayerNorm(affine) -> next GEMM's operand.
-  constexpr int D = NH * 64;
-  constexpr int NV = D / 32;
-  __shared__ __align__(16) float xs[4][D];
-  const int chunks_per_seq = (T + 3) >> 2;
-  const int n = blockIdx.x / chunks_per_seq;
-  const int c0 = (blockIdx.x - n * chunks_per_seq) * 4;
-  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    const int qi = lane >> 3, dsub = lane & 7;
-    const int ce = min(c0 + 4, T);
-    const int t = min(c0 + qi, T - 1);            // ragged last chunk: surplus query groups recompute the last row
-    const int ks0 = max(0, c0 - window + 1);       // first key any query of the chunk may see (query c0)
-    const int ks = min(c0, max(0, t - window + 1));
-    const int nk = ce - ks0;                       // <= MAXK
-    const int skip = ks - ks0;                     // keys [ks0, ks) are outside this query's window
-    const size_t row = (size_t)n * T + t;
-    const float* qrow = qkv + row * (3 * D) + hd * 64 + dsub * 4;
-    const float* kbase = qkv + ((size_t)n * T + ks0) * (3 * D) + D + hd * 64 + dsub * 4;
-    const float* vbase = kbase + D;
-    float4 q0 = *reinterpret_cast<const float4*>(qrow);
-    float4 q1 = *reinterpret_cast<const float4*>(qrow + 32);
-    const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
-    const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
-    // scores are kept in the log2 domain: q is scaled by log2(e) / sqrt(64) once, so softmax needs only ex2
-    const float qs = 0.125f * 1.4426950408889634f;
-    const float2 qa = make_float2(q0.x * qs, q0.y * qs), qb = make_float2(q0.z * qs, q0.w * qs);
-    const float2 qc = make_float2(q1.x * qs, q1.y * qs), qd = make_float2(q1.z * qs, q1.w * qs);
-    float s[MAXK];
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      s[j] = 0.f;
-      if (j < nk) {
-        const float4 k0 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D));
-        const float4 k1 = *reinterpret_cast<const float4*>(kbase + (size_t)j * (3 * D) + 32);
-        float2 acc = __fmul2_rn(qa, make_float2(k0.x, k0.y));  // packed fp32x2 FMAs: two lanes of the dot product each
-        acc = __ffma2_rn(qb, make_float2(k0.z, k0.w), acc);
-        acc = __ffma2_rn(qc, make_float2(k1.x, k1.y), acc);
-        acc = __ffma2_rn(qd, make_float2(k1.z, k1.w), acc);
-        s[j] = acc.x + acc.y;
-      }
-    }
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      float v = s[j];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v = (j >= skip && j < nk) ? v : -INFINITY;
-      s[j] = v;
-      m = fmaxf(m, v);
-    }
-    float l = 0.f;
-    float2 o01 = make_float2(0.f, 0.f), o23 = o01, o45 = o01, o67 = o01;
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      if (j < nk) {
-        float p;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s[j] - m));  // 2^(-inf) = 0 for masked keys
-        l += p;
-        const float4 v0 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D));
-        const float4 v1 = *reinterpret_cast<const float4*>(vbase + (size_t)j * (3 * D) + 32);
-        const float2 pp = make_float2(p, p);
-        o01 = __ffma2_rn(pp, make_float2(v0.x, v0.y), o01);
-        o23 = __ffma2_rn(pp, make_float2(v0.z, v0.w), o23);
-        o45 = __ffma2_rn(pp, make_float2(v1.x, v1.y), o45);
-        o67 = __ffma2_rn(pp, make_float2(v1.z, v1.w), o67);
-      }
-    }
-    const float o[8] = {o01.x, o01.y, o23.x, o23.y, o45.x, o45.y, o67.x, o67.y};
-    const float inv = 1.0f / l;
-    float* xp = &xs[qi][hd * 64 + dsub * 4];
-    *reinterpret_cast<float4*>(xp) = make_float4(fmaf(o[0], inv, r0.x), fmaf(o[1], inv, r0.y), fmaf(o[2], inv, r0.z), fmaf(o[3], inv, r0.w));
-    *reinterpret_cast<float4*>(xp + 32) = make_float4(fmaf(o[4], inv, r1.x), fmaf(o[5], inv, r1.y), fmaf(o[6], inv, r1.z), fmaf(o[7], inv, r1.w));
-  }
-  __syncthreads();
-  const int qi = hd;  // phase 2: warp w normalises query row w
-  if (qi >= 4 || c0 + qi >= T) return;
-  const size_t row = (size_t)n * T + c0 + qi;
-  float x[NV];
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(&xs[qi][(i * 32 + lane) * 4]);
-    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-  }
-  float mean, rstd;
-  row_stats<NV>(x, D, mean, rstd);
-  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const int e = (i * 32 + lane) * 4;
-    const float4 al = *reinterpret_cast<const float4*>(ap + e);
-    const float4 be = *reinterpret_cast<const float4*>(ap + D + e);
-    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
-    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
-    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
-    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
-    *reinterpret_cast<float4*>(h + row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-  }
-  row_stats<NV>(x, D, mean, rstd);
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const int e = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(g3 + e);
-    const float4 bb = *reinterpret_cast<const float4*>(b3 + e);
-    float4 o;
-    o.x = (x[4 * i + 0] - mean) * rstd * g.x + bb.x;
-    o.y = (x[4 * i + 1] - mean) * rstd * g.y + bb.y;
-    o.z = (x[4 * i + 2] - mean) * rstd * g.z + bb.z;
-    o.w = (x[4 * i + 3] - mean) * rstd * g.w + bb.w;
-    store_operand4(a_out, row * D + e, o);
-  }
-}
-
-// Same computation with the key/value rows of the chunk staged in shared memory by bulk async copies: row j of the
-// QKV buffer holds K | V contiguously (2 D floats = 4 KB at D = 512), so one elected thread issues one
-// cp.async.bulk per visible key row against an mbarrier and the whole block waits ONCE, instead of every warp walking
-// ~15 dependent L2 round trips (with <= 64 registers per thread the compiler cannot keep 2 x 11 float4 loads in
-// flight, see the SASS of the kernel above).  The score / softmax / PV loops then read shared memory (8 lanes of a
-// query read 128 contiguous bytes, the 4 query groups broadcast).  Dynamic smem: mk * 2D + 4D floats + one mbarrier.
-template <int NH, int MAXK>
-__global__ void __launch_bounds__(NH * 32, 32 / NH)
-attn_chunk4_bulk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
-                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
-                        const float* __restrict__ g3, const float* __restrict__ b3, int n_seq, int T, int window,
-                        int* zero_flags, int n_zero) {
-  constexpr int D = NH * 64;
-  constexpr int NV = D / 32;
-  extern __shared__ __align__(128) uint8_t attn_smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(attn_smem);
-  float* xs = reinterpret_cast<float*>(attn_smem + 128);  // [4][D]
-  float* kv = xs + 4 * D;                                   // [mk][2 D]: K | V of key row ks0 + j
-  const int chunks_per_seq = (T + 3) >> 2;
-  const int n = blockIdx.x / chunks_per_seq;
-  const int c0 = (blockIdx.x - n * chunks_per_seq) * 4;
-  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ce = min(c0 + 4, T);
-  const int ks0 = max(0, c0 - window + 1);
-  const int nk = ce - ks0;  // <= MAXK
-  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  pdl_wait();
-  pdl_trigger();
-  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
-  if (threadIdx.x == 0) {
-    const uint32_t row_bytes = 2 * D * sizeof(float);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * nk) : "memory");
-    const float* src = qkv + ((size_t)n * T + ks0) * (3 * D) + D;
-    uint32_t dst = (uint32_t)__cvta_generic_to_shared(kv);
-    for (int j = 0; j < nk; ++j) {
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar_s) : "memory");
-      src += 3 * D;
-      dst += row_bytes;
-    }
-  }
-  {
-    const int qi = lane >> 3, dsub = lane & 7;
-    const int t = min(c0 + qi, T - 1);
-    const int ks = min(c0, max(0, t - window + 1));
-    const int skip = ks - ks0;
-    const size_t row = (size_t)n * T + t;
-    const float* qrow = qkv + row * (3 * D) + hd * 64 + dsub * 4;
-    float4 q0 = *reinterpret_cast<const float4*>(qrow);
-    float4 q1 = *reinterpret_cast<const float4*>(qrow + 32);
-    const float4 r0 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4);
-    const float4 r1 = *reinterpret_cast<const float4*>(h + row * D + hd * 64 + dsub * 4 + 32);
-    const float qs = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64): softmax in the log2 domain
-    const float2 qa = make_float2(q0.x * qs, q0.y * qs), qb = make_float2(q0.z * qs, q0.w * qs);
-    const float2 qc = make_float2(q1.x * qs, q1.y * qs), qd = make_float2(q1.z * qs, q1.w * qs);
-    __syncthreads();  // mbarrier initialised before anyone polls it
-    {
-      uint32_t ok = 0;
-      while (!ok) {
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok) : "r"(bar_s) : "memory");
-      }
-    }
-    const float* kb = kv + hd * 64 + dsub * 4;
-    float sc[MAXK];
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      sc[j] = 0.f;
-      if (j < nk) {
-        const float4 k0 = *reinterpret_cast<const float4*>(kb + j * (2 * D));
-        const float4 k1 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + 32);
-        float2 acc = __fmul2_rn(qa, make_float2(k0.x, k0.y));
-        acc = __ffma2_rn(qb, make_float2(k0.z, k0.w), acc);
-        acc = __ffma2_rn(qc, make_float2(k1.x, k1.y), acc);
-        acc = __ffma2_rn(qd, make_float2(k1.z, k1.w), acc);
-        sc[j] = acc.x + acc.y;
-      }
-    }
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      float v = sc[j];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v = (j >= skip && j < nk) ? v : -INFINITY;
-      sc[j] = v;
-      m = fmaxf(m, v);
-    }
-    float l = 0.f;
-    float2 o01 = make_float2(0.f, 0.f), o23 = o01, o45 = o01, o67 = o01;
-#pragma unroll
-    for (int j = 0; j < MAXK; ++j) {
-      if (j < nk) {
-        float p;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(sc[j] - m));
-        l += p;
-        const float4 v0 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + D);
-        const float4 v1 = *reinterpret_cast<const float4*>(kb + j * (2 * D) + D + 32);
-        const float2 pp = make_float2(p, p);
-        o01 = __ffma2_rn(pp, make_float2(v0.x, v0.y), o01);
-        o23 = __ffma2_rn(pp, make_float2(v0.z, v0.w), o23);
-        o45 = __ffma2_rn(pp, make_float2(v1.x, v1.y), o45);
-        o67 = __ffma2_rn(pp, make_float2(v1.z, v1.w), o67);
-      }
-    }
-    const float inv = 1.0f / l;
-    float* xp = xs + qi * D + hd * 64 + dsub * 4;
-    *reinterpret_cast<float4*>(xp) = make_float4(fmaf(o01.x, inv, r0.x), fmaf(o01.y, inv, r0.y), fmaf(o23.x, inv, r0.z), fmaf(o23.y, inv, r0.w));
-    *reinterpret_cast<float4*>(xp + 32) = make_float4(fmaf(o45.x, inv, r1.x), fmaf(o45.y, inv, r1.y), fmaf(o67.x, inv, r1.z), fmaf(o67.y, inv, r1.w));
-  }
-  __syncthreads();
-  const int qi = hd;  // phase 2: warp w normalises query row w
-  if (qi >= 4 || c0 + qi >= T) return;
-  const size_t row = (size_t)n * T + c0 + qi;
-  float x[NV];
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(xs + qi * D + (i * 32 + lane) * 4);
-    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-  }
-  float mean, rstd;
-  row_stats<NV>(x, D, mean, rstd);
-  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off;
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const int e = (i * 32 + lane) * 4;
-    const float4 al = *reinterpret_cast<const float4*>(ap + e);
-    const float4 be = *reinterpret_cast<const float4*>(ap + D + e);
-    x[4 * i + 0] = (x[4 * i + 0] - mean) * rstd * (1.f + al.x) + be.x;
-    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * (1.f + al.y) + be.y;
-    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * (1.f + al.z) + be.z;
-    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * (1.f + al.w) + be.w;
-    *reinterpret_cast<float4*>(h + row * D + e) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-  }
-  row_stats<NV>(x, D, mean, rstd);
-#pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const int e = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(g3 + e);
-    const float4 bb = *reinterpret_cast<const float4*>(b3 + e);
-    float4 o;
-    o.x = (x[4 * i + 0] - mean) * rstd * g.x + bb.x;
-    o.y = (x[4 * i + 1] - mean) * rstd * g.y + bb.y;
-    o.z = (x[4 * i + 2] - mean) * rstd * g.z + bb.z;
-    o.w = (x[4 * i + 3] - mean) * rstd * g.w + bb.w;
-    store_operand4(a_out, row * D + e, o);
-  }
-}
-
 // -------------------------------------------------------------------------------------------
 // Register-tiled variant: ONE WARP per attention chunk, all heads at once.  Lane = (head hd = lane / LPH, slice
 // dq = lane % LPH) with LPH = 32 / NH lanes per head; the lane owns F = 16 / LPH float4 groups of its head,

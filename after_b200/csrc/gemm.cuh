@@ -54,8 +54,8 @@ struct GemmEpi {
   int stat_groups = 0;
   int stat_cpg = 1;                  // channels per group
   int stat_cmod = 0;                 // channel = n % stat_cmod (transposed conv: several phases share channels)
-  int debug_skip = 0;                // profiling experiments only: 1 = drop the epilogue's global traffic
-  unsigned long long* debug_ts = nullptr;  // profiling experiments only: %globaltimer marks of CTA 0
+  int debug_skip = 0;                // -DAFTER_DEBUG builds only: 1 = drop the epilogue's global traffic, 2 = no operand loads, 4 = no MMAs
+  unsigned long long* debug_ts = nullptr;  // -DAFTER_DEBUG builds only: %globaltimer marks of CTA 0
 };
 
 // vals: NV consecutive columns [col0, col0+NV) of frame t of batch b; col0 % 4 == 0, NV % 4 == 0.
@@ -449,7 +449,7 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
       x.z = a1 * cs.z - b1 * cs.w; x.w = b1 * cs.z + a1 * cs.w;
     }
     if (has_res) { x.x += aux.a[i].x; x.y += aux.a[i].y; x.z += aux.a[i].z; x.w += aux.a[i].w; }
-    if ((FULL || r < nvalid) && !(e.debug_skip & 1)) {
+    if ((FULL || r < nvalid) && !(kDebugBuild && (e.debug_skip & 1))) {
       if (MODE == EPI_PLAIN) {
         ssum += (x.x + x.y) + (x.z + x.w);
         ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
@@ -658,7 +658,7 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 //   warps 2-5 : epilogue (tcgen05.ld -> epi_store); their arrival on the leader's `tmem_empty` recycles the buffer
 // =====================================================================================
 __device__ __forceinline__ void ts_mark(const GemmEpi& e, int slot) {
-  if (e.debug_ts && blockIdx.x == 0) {
+  if (kDebugBuild && e.debug_ts && blockIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     e.debug_ts[slot] = t;
@@ -804,7 +804,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             mbar_wait(&empty[s], par ^ 1);
             uint8_t* st = tiles + (size_t)s * stage_bytes;
             const uint32_t fb = mapa(smem_u32(&full[s]), 0);
-            if (epi.debug_skip & 2) {  // experiment: no operand traffic at all
+            if (kDebugBuild && (epi.debug_skip & 2)) {  // experiment: no operand traffic at all
               if (rank == 0) mbar_expect_tx(&full[s], 0);
               continue;
             }
@@ -839,7 +839,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + A_BYTES);
           const uint64_t a_lo = make_smem_desc(st + A_BYTES + B_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
           uint32_t accum = kb > 0;
-          if (epi.debug_skip & 4) {  // experiment: no MMAs
+          if (kDebugBuild && (epi.debug_skip & 4)) {  // experiment: no MMAs
             umma2_commit_mc(&empty[s]);
             continue;
           }
@@ -879,7 +879,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int c = cbeg; c < cbeg + QCOLS; c += 16) {
           EpiAux aux;
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!(epi.debug_skip & 1)) {
+          if (!(kDebugBuild && (epi.debug_skip & 1))) {
             epi_prefetch<MODE>(epi, aux, b, t_base, T, n0 + c, lane);  // in flight during the TMEM load
             if (epi.bias) bias4 = *reinterpret_cast<const float4*>(epi.bias + n0 + c + (lane & 3) * 4);
           }
@@ -962,7 +962,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS_MLP, 1)
 mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_constant__ LinearProblem p1, int T, int nprod,
                      int m_tiles_per_b, int* __restrict__ flags, int flag_need, unsigned long long* dbg) {
   auto mark = [&](int slot) {  // profiling experiments only: per-cluster %globaltimer marks of the leader CTA
-    if (dbg && (blockIdx.x & 1) == 0) {
+    if (kDebugBuild && dbg && (blockIdx.x & 1) == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       dbg[(blockIdx.x >> 1) * 16 + slot] = t;

@@ -85,7 +85,7 @@ inline int pick_bn2(int N, int n_per_phase) {
 inline bool use_pair_kernel() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AFTER_GEMM");
+    const char* e = debug_env("AFTER_GEMM");
     v = (e && std::string(e) == "1cta") ? 0 : 1;
   }
   return v == 1;
@@ -231,7 +231,7 @@ inline void tc_init_kernels() {
 inline bool use_fused_mlp() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AFTER_FUSED_MLP");
+    const char* e = debug_env("AFTER_FUSED_MLP");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -241,7 +241,7 @@ inline bool use_fused_mlp() {
 inline int mlp_ksplit() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("AFTER_MLP_KSPLIT");
+    const char* e = debug_env("AFTER_MLP_KSPLIT");
     v = (e && e[0] == '1') ? 1 : 2;
   }
   return v;
@@ -270,7 +270,7 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   epi0.bias = W0.bias;
   epi1.bias = W2.bias;
   {
-    const char* e = getenv("AFTER_DEBUG_SKIP_EPILOGUE");
+    const char* e = debug_env("AFTER_DEBUG_SKIP_EPILOGUE");
     if (e) epi0.debug_skip = epi1.debug_skip = atoi(e);
   }
   tc::LinearProblem p0, p1;
@@ -299,7 +299,7 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   static int trace = -1;
   static unsigned long long* dbg = nullptr;
   if (trace < 0) {
-    const char* e = getenv("AFTER_DEBUG_TRACE_MLP");
+    const char* e = debug_env("AFTER_DEBUG_TRACE_MLP");
     trace = e ? atoi(e) : 0;  // trace the n-th fused launch (1-based), run with AFTER_NO_GRAPH=1
     if (trace > 0) AFTER_CUDA_CHECK(cudaMalloc(&dbg, 128 * 16 * sizeof(unsigned long long)));
   }
@@ -340,7 +340,7 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
   epi.bias = W.bias;
   {
     static int skip = -1;
-    if (skip < 0) { const char* e = getenv("AFTER_DEBUG_SKIP_EPILOGUE"); skip = e ? atoi(e) : 0; }
+    if (skip < 0) { const char* e = debug_env("AFTER_DEBUG_SKIP_EPILOGUE"); skip = e ? atoi(e) : 0; }
     epi.debug_skip = skip;
   }
   // algorithmic work of this launch: 2*M*N*K flops; operand read once + result written once (+ residual read)
@@ -432,7 +432,7 @@ inline void debug_gemm(const float* A, const float* W, const float* bias, float*
       }
     }
     GemmEpi e; e.out_f32 = C; e.ldo = N;
-    const char* tr = getenv("AFTER_DEBUG_TRACE");
+    const char* tr = debug_env("AFTER_DEBUG_TRACE");
     unsigned long long* ts = nullptr;
     if (tr && tr[0] == '1') {
       ts = tmp.alloc<unsigned long long>(32);

@@ -347,6 +347,14 @@ def ecapa_state_dict(cfg: EcapaConfig, seed: int = 0) -> StateDict:
 
 
 # ----------------------------------------------------------------------------- inputs
+def synth_inputs_per_stream(batch: int, cfg: DenoiserConfig, seed: int = 1234, frames: int = None, first: int = 0):
+    """Like ``synth_inputs`` but stream ``b`` is drawn from its own generator (seed + first + b): stream b's inputs do not
+    depend on how many streams are generated with it, so a 1-GPU run (8 streams) and an 8-GPU run (64 streams) agree on the
+    streams they share -- what lets ``bench.py`` publish a checksum that must not change with the GPU count."""
+    parts = [synth_inputs(1, cfg, seed=seed + first + b, frames=frames) for b in range(batch)]
+    return tuple(torch.cat([p[i] for p in parts]) for i in range(3))
+
+
 def synth_inputs(batch: int, cfg: DenoiserConfig, seed: int = 1234, frames: int = None):
     """x0 / cond / time_cond the way SURVEY.md section 8d prescribes (host-generated, so that
     1-GPU and N-GPU runs see identical streams)."""

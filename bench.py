@@ -9,6 +9,11 @@ One bench "step" = one ``RectifiedFlow.sample`` call (50 diffusion steps over th
 ``value`` = diffusion-steps/s summed over GPUs (each GPU integrates its own 8 streams: weak scaling), inputs
 resident in HBM; ``e2e`` = the same through the host-buffer C-ABI entry (pinned host tensors, H2D + D2H inside);
 ``rtf`` = real-time factor of the full chain (2x encode, structure encoder, sample, decode).
+``configs`` = the other BASELINE.json configurations at their per-GPU sizes, each with its own roofline block:
+``config3_bf16`` (base, bf16, 8 streams/GPU), ``config4_midi`` (midi model + MIDI CFG layout, 8 streams/GPU),
+``config5_codec`` (AutoEncoder encode + decode only, 1..16 streams/GPU, GB/s against the byte model of SURVEY.md 8d).
+``checksum`` = CRC32 of the sampled latents per stream: streams are generated per-stream-seeded on the host, so the
+CRCs of streams 0..7 must be identical for every --gpus N (N-independence of the shard + gather).
 """
 import argparse
 import json
@@ -18,6 +23,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -25,6 +31,10 @@ sys.path.insert(0, ROOT)
 CHUNK = 524288
 SR = 44100
 FLOP_PER_SEQ = {"base": 7.36e9, "tiny": 1.86e9, "midi": 7.75e9}
+# codec byte / flop model per 524288-sample chunk: every conv reads its input once and writes its
+# output once, everything else fused
+AE_BYTES = {"encode": {"fp32": 475e6, "bf16": 238e6}, "decode": {"fp32": 620e6, "bf16": 310e6}}
+AE_FLOPS = {"encode": 45.1e9, "decode": 95.3e9}
 
 
 def peaks():
@@ -89,7 +99,7 @@ class ClockSampler:
 def synth_setup(name, B_total):
     from after_b200 import config, synth
     mc = config.get_config(name)
-    x0, cond, tc = synth.synth_inputs(B_total, mc.denoiser, seed=1234)
+    x0, cond, tc = synth.synth_inputs_per_stream(B_total, mc.denoiser, seed=1234)  # stream b independent of B_total
     return mc, x0, cond, tc
 
 
@@ -149,7 +159,62 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # ms_per_step is scaled from the bounded sample to the full nb_steps (every Euler step is identical work);
+        # value (steps/s) is a measured rate, not extrapolated
+        "extrapolated": True, "measured_ms_per_step": dt / args.steps * 1e3, "measured_diffusion_steps_per_step": sample_steps,
     }))
+
+
+def crc32(t):
+    return zlib.crc32(t.detach().float().cpu().contiguous().numpy().tobytes()) & 0xffffffff
+
+
+def codec_traffic():
+    """DRAM bytes per launch of the codec kernel classes from the committed ncu --set full capture (profiles/), or None."""
+    tr = os.path.join(ROOT, "profiles", "traffic_codec.json")
+    if not os.path.exists(tr):
+        return None
+    with open(tr) as fh:
+        return json.load(fh)
+
+
+def gemm_roofline(eng, run, precision, pk):
+    """Per-class CUDA-event timing of one ``run()`` (graph bypassed) -> (roofline block of the dominant GEMM kernel, classes)."""
+    eng.profile(True)
+    run()
+    prof = eng.profile_read()
+    eng.profile(False)
+    tc_mode = precision != "fp32_simt"
+    dom = "mlp_fused" if (tc_mode and prof["mlp_fused"]["launches"]) else ("tap_gemm_tc" if tc_mode else "tap_gemm_simt")
+    g = prof[dom]
+    tot_prof = sum(v["ms"] for v in prof.values())
+    if not g["launches"]:
+        return None, prof
+    ach = g["flops"] / (g["ms"] / 1e3) / 1e12
+    issued = 3 if precision == "fp32" else 1
+    kname = {"mlp_fused": "mlp_fused_tc2_kernel<256> (MLP up + down projection, one persistent CTA-pair tcgen05 launch)",
+             "tap_gemm_tc": "tap_gemm_tc2_kernel (CTA-pair tcgen05 tap-GEMM)", "tap_gemm_simt": "tap_gemm_simt_kernel"}[dom]
+    roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": kname,
+            "launches_per_sample": g["launches"], "avg_launch_us": g["ms"] * 1e3 / g["launches"],
+            "flops_per_launch": g["flops"] / g["launches"], "share_of_profiled_ms": g["ms"] / tot_prof,
+            "issued_mma_per_product": issued, "issued_frac": ach * issued / pk["bf16_sustained"],
+            "peak_source": pk["source"] + ", bf16 sustained",
+            "how": "algorithmic 2*M*(N0*K0 + N2*K2) flops per launch / mean CUDA-event duration of the launches of one "
+                   "sample() call on the library's work stream (graph bypassed, PDL off between events)"}
+    if dom == "mlp_fused":
+        q = prof["tap_gemm_tc"]
+        if q["launches"]:
+            roof["other_gemm_class"] = {"kernel": "tap_gemm_tc2_kernel (QKV + out-proj)", "launches": q["launches"],
+                                        "achieved": q["flops"] / (q["ms"] / 1e3) / 1e12,
+                                        "frac": q["flops"] / (q["ms"] / 1e3) / 1e12 / pk["bf16_sustained"]}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as fh:
+            tj = json.load(fh)
+        roof["traffic"] = tj.get("tc::mlp_fused_tc2_kernel<256>_bytes_per_launch" if dom == "mlp_fused" else "tap_gemm_tc_kernel_bytes_per_launch")
+        roof["traffic_source"] = tj.get("source")
+    return roof, prof
 
 
 def main():
@@ -165,6 +230,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chain", action="store_true", help="skip the full-chain RTF leg")
     ap.add_argument("--no-stream", action="store_true", help="skip the streaming-block latency leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs for BASELINE configs 3/4/5 (bf16, midi, codec sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -310,42 +376,122 @@ def main():
 
     # ---- roofline of the dominant kernel (tcgen05 tap-GEMM), per-launch CUDA events on the launching stream ----------
     pk = peaks()
-    roof = None
-    prof = None
+    roof, prof = (None, None)
     if rank == 0:
-        eng.profile(True)
-        eng.sample(x0, cond, tc, NS, 2.0, 1.0)
-        prof = eng.profile_read()
-        eng.profile(False)
-        tc_mode = args.precision != "fp32_simt"
-        dom = "mlp_fused" if (tc_mode and prof["mlp_fused"]["launches"]) else ("tap_gemm_tc" if tc_mode else "tap_gemm_simt")
-        g = prof[dom]
-        tot_prof = sum(v["ms"] for v in prof.values())
-        if g["launches"]:
-            ach = g["flops"] / (g["ms"] / 1e3) / 1e12
-            issued = 3 if args.precision == "fp32" else 1
-            kname = {"mlp_fused": "mlp_fused_tc2_kernel<256> (MLP up + down projection, one persistent CTA-pair tcgen05 launch)",
-                     "tap_gemm_tc": "tap_gemm_tc2_kernel (CTA-pair tcgen05 tap-GEMM)", "tap_gemm_simt": "tap_gemm_simt_kernel"}[dom]
-            roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": kname,
-                    "launches_per_sample": g["launches"], "avg_launch_us": g["ms"] * 1e3 / g["launches"],
-                    "flops_per_launch": g["flops"] / g["launches"], "share_of_profiled_ms": g["ms"] / tot_prof,
-                    "issued_mma_per_product": issued, "issued_frac": ach * issued / pk["bf16_sustained"],
-                    "peak_source": pk["source"] + ", bf16 sustained",
-                    "how": "algorithmic 2*M*(N0*K0 + N2*K2) flops per launch / mean CUDA-event duration of the launches of one "
-                           "sample() call on the library's work stream (graph bypassed, PDL off between events)"}
-            if dom == "mlp_fused":
-                q = prof["tap_gemm_tc"]
-                if q["launches"]:
-                    roof["other_gemm_class"] = {"kernel": "tap_gemm_tc2_kernel (QKV + out-proj)", "launches": q["launches"],
-                                                "achieved": q["flops"] / (q["ms"] / 1e3) / 1e12,
-                                                "frac": q["flops"] / (q["ms"] / 1e3) / 1e12 / pk["bf16_sustained"]}
-            tr = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tr):
-                with open(tr) as fh:
-                    tj = json.load(fh)
-                roof["traffic"] = tj.get("tc::mlp_fused_tc2_kernel<256>_bytes_per_launch" if dom == "mlp_fused" else "tap_gemm_tc_kernel_bytes_per_launch")
-                roof["traffic_source"] = tj.get("source")
+        roof, prof = gemm_roofline(eng, lambda: eng.sample(x0, cond, tc, NS, 2.0, 1.0), args.precision, pk)
+
+    # ---- output checksums: per-stream CRC32 of the sampled latents; streams 0..7 must not depend on --gpus ------------
+    out_local = eng.sample(x0, cond, tc, NS, 2.0, 1.0)
+    gathered = parallel.gather_streams(out_local, B * world)
+    torch.cuda.synchronize()
+    local_crcs = [crc32(out_local[i]) for i in range(out_local.shape[0])]
+    if world > 1:
+        all_crcs = [None] * world
+        dist.all_gather_object(all_crcs, local_crcs)
+        all_crcs = [c for part in all_crcs for c in part]
+    else:
+        all_crcs = local_crcs
+    checksum = None
+    if rank == 0:
+        checksum = {"algo": "crc32 of the fp32 latents of each stream after the 50-step sample (host-seeded per stream)",
+                    "streams_0_7": [f"{c:08x}" for c in all_crcs[:8]],
+                    "all_streams": f"{zlib.crc32(' '.join(f'{c:08x}' for c in all_crcs).encode()) & 0xffffffff:08x}",
+                    "gathered_equals_shards": all(crc32(gathered[i]) == all_crcs[i] for i in range(B * world)),
+                    "n_streams": B * world}
+
+    # ---- the other BASELINE.json configurations (per-GPU sizes), each with its own roofline block --------------------
+    configs = None
+    if not args.no_configs:
+        configs = {}
+
+        def sampler_leg(model_name, precision, variant, g_t, g_s, clamp, what):
+            mcl, xa, ca, ta = synth_setup(model_name, B * world)
+            xs, cs, ts = (t.to(dev) for t in parallel.shard([xa, ca, ta], world, rank))
+            e = Engine(model=mcl, denoiser_state=synth.denoiser_state_dict(mcl.denoiser, 0), precision=precision, device=local,
+                       max_batch=B, max_steps=NS)
+
+            def run():
+                return e.sample(xs, cs, ts, NS, g_t, g_s, cfg_variant=variant, clamp=clamp)
+
+            def step():
+                return parallel.gather_streams(run(), B * world)
+
+            for _ in range(3):
+                step()
+            ms, _ = timed(step, args.steps)
+            v = NS * args.steps * world / (ms / 1e3)
+            leg = {"workload": what, "metric": "diffusion-steps/sec", "value": v, "unit": "steps/s", "ms_per_step": ms / args.steps,
+                   "precision": precision, "batch_per_gpu": B, "global_batch": B * world, "nb_steps": NS,
+                   "algorithmic_tflops": 3 * B * FLOP_PER_SEQ[model_name] * NS * args.steps * world / (ms / 1e3) / 1e12}
+            if rank == 0:
+                leg["roofline"], kp = gemm_roofline(e, run, precision, pk)
+                leg["kernel_profile_ms"] = {k: round(v_["ms"], 3) for k, v_ in kp.items()}
+            e.close()
+            return leg
+
+        if args.precision != "bf16" or args.model != "base":
+            configs["config3_bf16"] = sampler_leg("base", "bf16", 0, 2.0, 1.0, 0.01,
+                                                  f"BASELINE configs[2]: base audio-to-audio, bf16, batch={B}/GPU ({B * world} total), {NS} steps")
+        if args.model != "midi":
+            configs["config4_midi"] = sampler_leg("midi", args.precision, 1, 2.0, 3.0, 0.1,
+                                                  f"BASELINE configs[3]: midi (128-pitch piano roll, window 16, MIDI CFG layout), "
+                                                  f"batch={B}/GPU ({B * world} total), {NS} steps")
+
+        # configs[4]: AutoEncoder encode + decode only, HBM GB/s sweep over the per-GPU batch
+        def codec_leg(precision):
+            a_sd = ae_sd if ae_sd is not None else synth.autoencoder_state_dict(acfg, 0)
+            e = Engine(autoencoder=acfg, autoencoder_state=a_sd, precision=precision, device=local, max_batch=16, max_samples=CHUNK)
+            rows = []
+            bm = "bf16" if precision == "bf16" else "fp32"
+            for b in (1, 2, 4, 8, 16):
+                audio = synth.synth_audio(b, CHUNK, seed=7 + rank).to(dev)
+                z = e.ae_encode(audio)
+                for _ in range(3):
+                    e.ae_encode(audio)
+                    e.ae_decode(z)
+                ms_e, _ = timed(lambda: e.ae_encode(audio), args.steps)
+                ms_d, _ = timed(lambda: e.ae_decode(z), args.steps)
+                te, td = ms_e / args.steps / 1e3, ms_d / args.steps / 1e3
+                rows.append({"batch_per_gpu": b, "global_batch": b * world, "encode_ms": te * 1e3, "decode_ms": td * 1e3,
+                             "encode_GBps": AE_BYTES["encode"][bm] * b / te / 1e9, "decode_GBps": AE_BYTES["decode"][bm] * b / td / 1e9,
+                             "encode_frac_hbm": AE_BYTES["encode"][bm] * b / te / 1e9 / pk["hbm_gbs"],
+                             "decode_frac_hbm": AE_BYTES["decode"][bm] * b / td / 1e9 / pk["hbm_gbs"],
+                             "encode_TFLOPs": AE_FLOPS["encode"] * b / te / 1e12, "decode_TFLOPs": AE_FLOPS["decode"] * b / td / 1e12,
+                             "chunks_per_s_all_gpus": b * world / (te + td), "rtf_encode_decode": b * world * (CHUNK / SR) / (te + td)})
+            leg = {"workload": "BASELINE configs[4]: AutoEncoder encode + decode only, 524288-sample chunks, batch/GPU sweep",
+                   "precision": precision, "byte_model": f"SURVEY.md 8d, {bm}: encode {AE_BYTES['encode'][bm] / 1e6:.0f} MB, decode "
+                   f"{AE_BYTES['decode'][bm] / 1e6:.0f} MB per chunk (each conv reads its input once, writes its output once)",
+                   "sweep": rows}
+            if rank == 0:  # per-kernel-class device time of one encode + decode at the largest batch (graph bypassed)
+                audio = synth.synth_audio(16, CHUNK, seed=7).to(dev)
+                z = e.ae_encode(audio)
+                e.profile(True)
+                e.ae_encode(audio)
+                e.ae_decode(z)
+                kp = e.profile_read()
+                e.profile(False)
+                tot = sum(v_["ms"] for v_ in kp.values()) or 1.0
+                g = kp["tap_gemm_tc"]
+                last = rows[-1]
+                leg["roofline"] = {
+                    "bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "peak_source": pk["source"] + ", copy bandwidth",
+                    "achieved": (AE_BYTES["encode"][bm] + AE_BYTES["decode"][bm]) * 16 / ((last["encode_ms"] + last["decode_ms"]) / 1e3) / 1e9,
+                    "kernel": "whole encode + decode at 16 chunks/GPU against the byte model (conv tap-GEMMs dominate)",
+                    "conv_class": {"launches": g["launches"], "ms": g["ms"], "share_of_profiled_ms": g["ms"] / tot,
+                                   "GBps": g["bytes"] / (g["ms"] / 1e3) / 1e9 if g["ms"] else None,
+                                   "TFLOPs": g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] else None},
+                    "act_operand_class": {"launches": kp["act_operand"]["launches"], "ms": kp["act_operand"]["ms"],
+                                          "share_of_profiled_ms": kp["act_operand"]["ms"] / tot,
+                                          "GBps": kp["act_operand"]["bytes"] / (kp["act_operand"]["ms"] / 1e3) / 1e9 if kp["act_operand"]["ms"] else None},
+                    "traffic": codec_traffic()}
+                leg["roofline"]["frac"] = leg["roofline"]["achieved"] / pk["hbm_gbs"]
+                leg["kernel_profile_ms"] = {k: round(v_["ms"], 3) for k, v_ in kp.items()}
+            e.close()
+            return leg
+
+        configs["config5_codec"] = codec_leg(args.precision)
+        if args.precision != "bf16":
+            configs["config5_codec_bf16"] = codec_leg("bf16")
 
     # ---- CPU baseline: the oracle port of the reference sampler on this box's host cores (rank 0, N = 1 only) --------
     cpu = None
@@ -367,6 +513,7 @@ def main():
             "sequence_steps_per_s": value * B,
             "algorithmic_tflops": 3 * B * FLOP_PER_SEQ[args.model] * NS * args.steps * world / (total_ms / 1e3) / 1e12,
             "e2e": e2e, "rtf": rtf, "stream": stream, "roofline": roof, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
+            "checksum": checksum, "configs": configs,
             "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in (prof or {}).items()},
         }
         print(json.dumps(line))

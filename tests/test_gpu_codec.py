@@ -8,8 +8,8 @@ from after_b200 import config, synth
 
 pytestmark = pytest.mark.gpu
 
-# bf16 (single-product) mode: random weights amplify rounding ~65x through the 79 convs; reported, loosely gated
-TOL = {"fp32": 1e-3, "fp32_simt": 1e-3, "bf16": 3e-1}
+# bf16 (single-product) mode: gate from SURVEY.md section 4.1 (audio rel-L2 <= 3e-2)
+TOL = {"fp32": 1e-3, "fp32_simt": 1e-3, "bf16": 3e-2}
 
 
 def rel(a, b):
@@ -50,8 +50,9 @@ def test_codec_matches_reference(golden, tag, precision):
         er = rel(rec, g["reconstructed"])
         print(f"codec_{tag} {precision}: encode {ez:.2e} decode {ey:.2e} reconstruct {er:.2e}")
         assert ez < TOL[precision] and ey < TOL[precision] and er < TOL[precision]
-        # replay of the captured graph is bit-identical
-        assert torch.equal(ae.decode(T(g["z_in"]).cuda()), y)
+        # replay of the captured graph: same kernels, but the GroupNorm sums are fp64 atomics whose order is not fixed,
+        # so equality is asserted to rounding, not bitwise
+        assert rel(ae.decode(T(g["z_in"]).cuda()), y) < 1e-6
     finally:
         eng.close()
 
@@ -154,17 +155,65 @@ def test_generate_chain_matches_oracle():
         eng.close()
 
 
-def test_codec_full_chunk_roundtrip_shape():
-    """The reference's own self-check (export_autoencoder.py:50-54) at the north-star chunk: 524288 samples ->
-    z (B, 64, 256) -> 524288 samples, finite."""
-    eng, sd, acfg = codec_engine("base", 2, "fp32", 2, 524288)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_codec_full_chunk_matches_oracle(precision):
+    """BASELINE chunk size: B = 2 x 524288 samples -> z (2, 64, 256) -> 524288 samples, VALUES against the CPU oracle
+    (AutoEncoder.encode / decode, SimpleNetsStream.py:918-954): GroupNorm over T = 32768 with cross-CTA fp64 atomics, the
+    128-frame TMA tile tails and the 256-frame PQMF at the size the RTF numbers are quoted on.  Also the reference's own
+    self-check (export_autoencoder.py:50-54): encode -> decode keeps the length."""
+    from oracle import after_oracle as O
+    eng, sd, acfg = codec_engine("base", 2, precision, 2, 524288)
     try:
-        audio = synth.synth_audio(2, 524288, seed=3).cuda()
-        z = eng.ae_encode(audio)
-        assert z.shape == (2, 64, 256)
-        y = eng.ae_decode(z)
-        assert y.shape == audio.shape
-        assert torch.isfinite(z).all() and torch.isfinite(y).all()
+        audio = synth.synth_audio(2, 524288, seed=3)
+        z_ref = O.ae_encode(sd, acfg, audio)
+        z = eng.ae_encode(audio.cuda())
+        assert z.shape == (2, 64, 256) and torch.isfinite(z).all()
+        ez = rel(z, z_ref)
+        zin = torch.randn(2, 64, 256, generator=torch.Generator().manual_seed(17))
+        y_ref = O.ae_decode(sd, acfg, zin)
+        y = eng.ae_decode(zin.cuda())
+        assert y.shape == audio.shape and torch.isfinite(y).all()
+        ey = rel(y, y_ref)
+        # encode -> decode round trip on the oracle's own latents (what the chain feeds the decoder)
+        er = rel(eng.ae_decode(z_ref.cuda()), O.ae_decode(sd, acfg, z_ref))
+        print(f"codec 2x524288 {precision}: encode {ez:.2e} decode {ey:.2e} decode(encode) {er:.2e}")
+        assert ez < TOL[precision] and ey < TOL[precision] and er < TOL[precision]
+    finally:
+        eng.close()
+
+
+def test_generate_chain_full_size_matches_oracle():
+    """The whole audio-to-audio chain at BASELINE configs[1] arithmetic: base models, 524288-sample chunks (T = 256), 50
+    Euler steps, CFG 2.0 / 1.0, B = 2 -- after_generate vs the oracle chain, on latents and on audio (north_star: 1e-3)."""
+    from after_b200.engine import Engine
+    from oracle import after_oracle as O
+    mc = config.get_config("base")
+    acfg = config.base_autoencoder()
+    sds = dict(den=synth.denoiser_state_dict(mc.denoiser, 0), ae=synth.autoencoder_state_dict(acfg, 0),
+               se=synth.encoder1d_state_dict(mc.structure_encoder, 0), te=synth.ecapa_state_dict(mc.timbre_encoder, 0))
+    B, steps, S = 2, 50, 524288
+    frames = S // acfg.ratio
+    eng = Engine(model=mc, autoencoder=acfg, denoiser_state=sds["den"], autoencoder_state=sds["ae"], structure_state=sds["se"],
+                 timbre_state=sds["te"], precision="fp32", max_batch=B, max_steps=steps, seq_len=frames, max_samples=S)
+    try:
+        a_s, a_t = synth.synth_audio(B, S, seed=41), synth.synth_audio(B, S, seed=42)
+        x0 = torch.randn(B, 64, frames, generator=torch.Generator().manual_seed(43))
+        z_s, z_t = O.ae_encode(sds["ae"], acfg, a_s), O.ae_encode(sds["ae"], acfg, a_t)
+        tcond = O.encoder1d_forward(sds["se"], mc.structure_encoder, z_s)
+        cond = O.ecapa_forward(sds["te"], mc.timbre_encoder, z_t)
+        x = O.sample(sds["den"], mc.denoiser, x0, cond, tcond, steps, 2.0, 1.0)
+        want = O.ae_decode(sds["ae"], acfg, x)
+        # stage by stage on the GPU (same calls the chain makes), then the one-call chain
+        g_zs, g_zt = eng.ae_encode(a_s.cuda()), eng.ae_encode(a_t.cuda())
+        g_tc, g_c = eng.structure_encode(g_zs), eng.timbre_encode(g_zt)
+        g_x = eng.sample(x0.cuda(), g_c, g_tc, steps, 2.0, 1.0)
+        e_lat = rel(g_x, x)
+        got = eng.generate(a_s.cuda(), a_t.cuda(), x0.cuda(), steps, 2.0, 1.0)
+        e_audio = rel(got, want)
+        print(f"chain base T=256 50 steps: z {rel(g_zs, z_s):.2e} time_cond {rel(g_tc, tcond):.2e} cond {rel(g_c, cond):.2e} "
+              f"latents {e_lat:.2e} audio {e_audio:.2e}")
+        assert e_lat < 1e-3 and e_audio < 1e-3
+        assert rel(eng.ae_decode(g_x), got) < 1e-5  # the one-call chain is the same computation
     finally:
         eng.close()
 

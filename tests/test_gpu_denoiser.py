@@ -142,39 +142,45 @@ def test_errors_are_loud():
 
 
 def test_baseline_config_parity_50_steps():
-    """BASELINE configs[1] arithmetic at full length: base, T = 256, 50 Euler steps, CFG 2.0/1.0, fp32 mode vs the CPU
-    oracle (2 of the 8 streams: rows are independent, see test_full_size_properties) -- tolerance 1e-3 (north_star);
-    the bf16 mode's drift over the same 50 steps is reported and loosely gated."""
+    """BASELINE configs[1] at FULL size: base, B = 8 streams (24 CFG rows), T = 256, 50 Euler steps, CFG 2.0/1.0, fp32 mode
+    vs the CPU oracle on ALL 8 streams (model.py:763-785) -- tolerance 1e-3 (north_star), per stream and overall; the
+    bf16 mode (BASELINE configs[2] arithmetic) is gated at 1e-2 on the same 50-step trajectory."""
     from oracle import after_oracle as O
-    eng, sd, mc = make_engine("base", 0, "fp32", 256, max_batch=2, max_steps=50)
+    B = 8
+    eng, sd, mc = make_engine("base", 0, "fp32", 256, max_batch=B, max_steps=50)
     try:
-        x0, cond, tc = synth.synth_inputs(2, mc.denoiser, seed=1234)
+        x0, cond, tc = synth.synth_inputs(B, mc.denoiser, seed=1234)
         want = O.sample(sd, mc.denoiser, x0, cond, tc, 50, 2.0, 1.0)
         got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 50, 2.0, 1.0)
         e = rel(got, want)
-        print(f"base T=256 50 steps fp32 mode: rel-L2 {e:.2e}")
-        assert e < 1e-3
+        per = [rel(got[b], want[b]) for b in range(B)]
+        print(f"base B=8 T=256 50 steps fp32 mode: rel-L2 {e:.2e} (worst stream {max(per):.2e})")
+        assert e < 1e-3 and max(per) < 1e-3
     finally:
         eng.close()
-    eng, sd, mc = make_engine("base", 0, "bf16", 256, max_batch=2, max_steps=50)
+    eng, sd, mc = make_engine("base", 0, "bf16", 256, max_batch=B, max_steps=50)
     try:
         got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 50, 2.0, 1.0)
         e = rel(got, want)
-        print(f"base T=256 50 steps bf16 mode: rel-L2 {e:.2e}")
-        assert e < 1e-1
+        per = [rel(got[b], want[b]) for b in range(B)]
+        print(f"base B=8 T=256 50 steps bf16 mode: rel-L2 {e:.2e} (worst stream {max(per):.2e})")
+        assert e < 1e-2 and max(per) < 2e-2
     finally:
         eng.close()
 
 
 def test_midi_config_full_length():
-    """BASELINE configs[3] arithmetic: midi (zs = 128 piano roll, window 16), MIDI CFG layout, T = 256."""
+    """BASELINE configs[3] arithmetic at full size: midi (zs = 128 piano roll, window 16), MIDI CFG layout
+    (export_midi.py:322-360, clamp 0.1), T = 256, 50 Euler steps, guidance 2.0 / 3.0."""
     from oracle import after_oracle as O
-    eng, sd, mc = make_engine("midi", 5, "fp32", 256, max_batch=2, max_steps=6)
+    eng, sd, mc = make_engine("midi", 5, "fp32", 256, max_batch=2, max_steps=50)
     try:
         x0, cond, tc = synth.synth_inputs(2, mc.denoiser, seed=77)
-        want = O.sample(sd, mc.denoiser, x0, cond, tc, 6, 2.0, 3.0, cfg_variant=1, clamp=0.1)
-        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 6, 2.0, 3.0, cfg_variant=1, clamp=0.1)
-        assert rel(got, want) < 1e-3
+        want = O.sample(sd, mc.denoiser, x0, cond, tc, 50, 2.0, 3.0, cfg_variant=1, clamp=0.1)
+        got = eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 50, 2.0, 3.0, cfg_variant=1, clamp=0.1)
+        e = rel(got, want)
+        print(f"midi T=256 50 steps fp32 mode: rel-L2 {e:.2e}")
+        assert e < 1e-3
     finally:
         eng.close()
 
