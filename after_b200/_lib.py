@@ -9,14 +9,14 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libafter_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_STAGES = 8
 
 OK, IGNORED = 0, 1
 PRECISION_FP32, PRECISION_BF16, PRECISION_FP32_SIMT = 0, 1, 2
 PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_simt": PRECISION_FP32_SIMT}
 DTYPE_F32, DTYPE_F64, DTYPE_I64 = 0, 1, 2
-MODULE_DENOISER, MODULE_AUTOENCODER, MODULE_STRUCTURE_ENCODER, MODULE_TIMBRE_ENCODER = 0, 1, 2, 3
+MODULE_DENOISER, MODULE_AUTOENCODER, MODULE_STRUCTURE_ENCODER, MODULE_TIMBRE_ENCODER, MODULE_UNET = 0, 1, 2, 3, 4
 CFG_AUDIO, CFG_MIDI = 0, 1
 KERNEL_CLASSES = {"tap_gemm_tc": 0, "tap_gemm_simt": 1, "attention": 2, "row_norm": 3, "act_operand": 4, "pqmf": 5,
                   "mlp_fused": 7}
@@ -70,6 +70,18 @@ class AfterConfig(C.Structure):
         ("te_global_context", C.c_int32),
         ("te_use_tanh", C.c_int32),
         ("max_cache_size", C.c_int32),
+        ("un_in_size", C.c_int32),
+        ("un_out_size", C.c_int32),
+        ("un_n_levels", C.c_int32),
+        ("un_channels", C.c_int32 * MAX_STAGES),
+        ("un_ratios", C.c_int32 * MAX_STAGES),
+        ("un_kernel_size", C.c_int32),
+        ("un_time_channels", C.c_int32),
+        ("un_time_cond_in_channels", C.c_int32),
+        ("un_time_cond_channels", C.c_int32),
+        ("un_cond_channels", C.c_int32),
+        ("un_n_attn_layers", C.c_int32),
+        ("un_use_res_last", C.c_int32),
     ]
 
 
@@ -87,6 +99,7 @@ PROTOTYPES = {
     "after_load_tensor": (C.c_int, [_H, C.c_int, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "after_finalize_weights": (C.c_int, [_H, C.c_int]),
     "after_denoiser_forward": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_unet_forward": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_model_forward": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "after_sample": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -8,6 +8,7 @@
 #include "context.cuh"
 #include "denoiser.cuh"
 #include "ecapa.cuh"
+#include "unet.cuh"
 
 namespace after {
 std::atomic<int64_t> g_launches{0};
@@ -20,14 +21,16 @@ struct after_ctx {
   after_config cfg{};
   int device = 0;
   int precision = -1;  // -1: weights not finalized
-  TensorMap tensors[4];
+  TensorMap tensors[5];
   Arena arena;
   StreamBridge bridge;
   Denoiser denoiser;
   Codec codec;
   StructureEncoder structure;
   TimbreEncoder timbre;
-  bool have_codec = false, have_structure = false, have_timbre = false;
+  UNet unet;
+  bool have_codec = false, have_structure = false, have_timbre = false, have_unet = false;
+  bool net_is_unet() const { return have_unet && denoiser.D == 0; }
   // device staging of the *_host entry points (the copies go straight from / to the caller's host pointers)
   float* dev_io = nullptr;
   size_t dev_io_floats = 0;
@@ -106,7 +109,7 @@ extern "C" {
 int after_abi_version(void) { return AFTER_B200_ABI_VERSION; }
 
 const char* after_build_info(void) {
-  return "libafter_b200 abi=2 arch=sm_100a (tcgen05/TMEM/TMA) nvcc=" AFTER_STR(__CUDACC_VER_MAJOR__) "." AFTER_STR(
+  return "libafter_b200 abi=3 arch=sm_100a (tcgen05/TMEM/TMA) nvcc=" AFTER_STR(__CUDACC_VER_MAJOR__) "." AFTER_STR(
       __CUDACC_VER_MINOR__) " built " __DATE__;
 }
 
@@ -157,6 +160,7 @@ int after_destroy(after_handle h) {
     cudaDeviceSynchronize();
     h->denoiser.destroy();
     h->codec.destroy();
+    h->unet.destroy();
     h->bridge.destroy();
     h->arena.release();
     if (h->dev_io) cudaFree(h->dev_io);
@@ -171,7 +175,7 @@ int after_load_tensor(after_handle h, int module, const char* key, const void* d
   int ignored = 0;
   int rc = guarded(h, [&] {
     AFTER_REQUIRE(h->precision < 0, AFTER_ESTATE, "weights already finalized");
-    AFTER_REQUIRE(module >= 0 && module < 4, AFTER_EINVAL, "unknown module id");
+    AFTER_REQUIRE(module >= 0 && module < 5, AFTER_EINVAL, "unknown module id");
     AFTER_REQUIRE(key && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 8, AFTER_EINVAL, "bad tensor arguments");
     const std::string k(key);
     // buffers the offline path never reads: streaming caches, unused position table, GroupNorm stream pads
@@ -226,6 +230,12 @@ int after_finalize_weights(after_handle h, int precision) {
       h->have_timbre = true;
       any = true;
     }
+    if (!h->tensors[AFTER_MODULE_UNET].empty()) {
+      AFTER_REQUIRE(h->cfg.un_n_levels > 0, AFTER_EINVAL, "UNET1D tensors loaded but after_config.un_n_levels == 0");
+      h->unet.finalize(h->cfg, h->tensors[AFTER_MODULE_UNET], precision, &h->arena);
+      h->have_unet = true;
+      any = true;
+    }
     AFTER_REQUIRE(any, AFTER_EMISSING, "no tensors were loaded");
     for (auto& m : h->tensors) m.clear();  // host copies are no longer needed
     h->precision = precision;
@@ -243,11 +253,29 @@ int after_denoiser_forward(after_handle h, const float* x, const float* time, co
   });
 }
 
+int after_unet_forward(after_handle h, const float* x, const float* time, const float* cond, const float* time_cond, float* out,
+                       int N, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_unet, AFTER_ESTATE, "no UNET1D weights on this handle");
+    AFTER_REQUIRE(x && time && out, AFTER_EINVAL, "null tensor pointer");
+    BridgeScope bridge(h->bridge, stream);
+    h->unet.forward(x, time, cond, time_cond, out, N, T, h->bridge.work);
+  });
+}
+
 int after_model_forward(after_handle h, const float* x, const float* time, const float* cond, const float* time_cond,
                         float* out, int B, int T, float guidance_timbre, float guidance_structure, int cfg_variant,
                         float clamp, void* stream) {
   return guarded(h, [&] {
     require_ready(h);
+    if (h->net_is_unet()) {
+      AFTER_REQUIRE(x && time && out, AFTER_EINVAL, "null tensor pointer");
+      BridgeScope bridge(h->bridge, stream);
+      h->unet.model_forward(x, time, cond, time_cond, out, B, T, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                            h->bridge.work);
+      return;
+    }
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x && time && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
     BridgeScope bridge(h->bridge, stream);
@@ -261,6 +289,13 @@ int after_sample(after_handle h, const float* x0, const float* cond, const float
                  void* stream) {
   return guarded(h, [&] {
     require_ready(h);
+    if (h->net_is_unet()) {
+      AFTER_REQUIRE(x0 && out, AFTER_EINVAL, "null tensor pointer");
+      BridgeScope bridge(h->bridge, stream);
+      h->unet.sample(x0, cond, time_cond, out, B, T, nb_steps, guidance_timbre, guidance_structure, cfg_variant, clamp,
+                     h->bridge.work);
+      return;
+    }
     AFTER_REQUIRE(h->denoiser.D > 0, AFTER_ESTATE, "no denoiser weights on this handle");
     AFTER_REQUIRE(x0 && cond && time_cond && out, AFTER_EINVAL, "null tensor pointer");
     BridgeScope bridge(h->bridge, stream);

@@ -168,16 +168,28 @@ struct ConvNet {
     const HostTensor& v = get(prefix + ".weight_v");
     AFTER_REQUIRE(v.shape.size() == 3 && v.shape[0] == cout && v.shape[1] == cin && v.shape[2] == k, AFTER_ESHAPE,
                   "tensor '" + prefix + ".weight_v' has an unexpected shape");
-    const std::vector<float> w = folded(prefix);
+    const HostTensor& b = get(prefix + ".bias");
+    AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
+    make_conv_from(L, folded(prefix), b.data.data(), cin, cout, k, taps, in_phases);
+  }
+  // plain (not weight-normed) nn.Conv1d: prefix.weight (cout, cin, k), prefix.bias   (unet1d.py, blocks.py)
+  void make_conv_plain(ConvLayer& L, const std::string& prefix, int cin, int cout, int k, const TapTable& taps, int in_phases) {
+    const HostTensor& w = get(prefix + ".weight");
+    AFTER_REQUIRE(w.shape.size() == 3 && w.shape[0] == cout && w.shape[1] == cin && w.shape[2] == k, AFTER_ESHAPE,
+                  "tensor '" + prefix + ".weight' has an unexpected shape");
+    const HostTensor& b = get(prefix + ".bias");
+    AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
+    make_conv_from(L, w.data, b.data.data(), cin, cout, k, taps, in_phases);
+  }
+  void make_conv_from(ConvLayer& L, const std::vector<float>& w, const float* bias, int cin, int cout, int k, const TapTable& taps,
+                      int in_phases) {
     // 16/32-channel inputs (both ends of the codec) are zero-padded to the 64-channel K granule of the tcgen05 path
     const int cp = (tc_mode() && cin < 64 && cin % 4 == 0 && cout % 32 == 0 && in_phases == 1) ? 64 : cin;
     std::vector<float> m((size_t)cout * k * cp, 0.f);
     for (int o = 0; o < cout; ++o)
       for (int c = 0; c < cin; ++c)
         for (int kk = 0; kk < k; ++kk) m[((size_t)o * k + kk) * cp + c] = w[((size_t)o * cin + c) * k + kk];
-    const HostTensor& b = get(prefix + ".bias");
-    AFTER_REQUIRE(b.numel() == cout, AFTER_ESHAPE, "tensor '" + prefix + ".bias' has an unexpected shape");
-    build_gemm_weight(L.w, *arena, m, b.data.data(), cout, cp, taps, tc_mode());
+    build_gemm_weight(L.w, *arena, m, bias, cout, cp, taps, tc_mode());
     L.cin = cin; L.cout = cout; L.in_phases = in_phases; L.out_phases = 1;
   }
 

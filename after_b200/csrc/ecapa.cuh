@@ -94,7 +94,7 @@ ecapa_conv_kernel(EcapaConvArgs a) {
   }
 }
 
-// out[b, co] = act(bias[co] + sum_ci W[co, ci] in[b, ci]);  act: 0 none, 1 ReLU, 2 sigmoid.  One warp per output.
+// out[b, co] = act(bias[co] + sum_ci W[co, ci] in[b, ci]);  act: 0 none, 1 ReLU, 2 sigmoid, 3 SiLU.  One warp per output.
 __global__ void vec_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                                   float* __restrict__ out, int B, int Cin, int Cout, int act) {
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -108,6 +108,7 @@ __global__ void vec_linear_kernel(const float* __restrict__ in, const float* __r
     s += bias ? bias[co] : 0.f;
     if (act == 1) s = fmaxf(s, 0.f);
     else if (act == 2) s = 1.0f / (1.0f + expf(-s));
+    else if (act == 3) s = s / (1.0f + expf(-s));
     out[o] = s;
   }
 }

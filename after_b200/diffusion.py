@@ -43,6 +43,25 @@ class DenoiserV2:
         return self
 
 
+class UNET1D:
+    """``net(x, time=, time_cond=, cond=)`` of the conv denoiser -- unet1d.py:376-429.  An engine created with ``unet`` /
+    ``unet_state`` runs ``RectifiedFlow.sample`` / ``model_forward`` over it."""
+
+    def __init__(self, engine: Engine):
+        if not engine.has_unet:
+            raise RuntimeError("engine was created without UNET1D weights")
+        self.engine = engine
+
+    def __call__(self, x, time=None, time_cond=None, cond=None, cache_index: int = 0):
+        return self.forward(x, time=time, time_cond=time_cond, cond=cond)
+
+    def forward(self, x, time=None, time_cond=None, cond=None):
+        return self.engine.unet_forward(x, time, cond, time_cond)
+
+    def eval(self):
+        return self
+
+
 class Encoder1D:
     """Structure encoder ``encoder_time(z)`` -- encoder.py:273-298."""
 

@@ -16,7 +16,7 @@ from .config import AutoEncoderConfig, DenoiserConfig, EcapaConfig, Encoder1DCon
 
 def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], max_batch: int, max_steps: int,
                  seq_len: Optional[int], max_samples: int, use_structure: bool, use_timbre: bool = False,
-                 max_cache_size: int = 0) -> L.AfterConfig:
+                 max_cache_size: int = 0, unet=None) -> L.AfterConfig:
     c = L.AfterConfig()
     c.abi_version = L.ABI_VERSION
     c.max_cache_size = max_cache_size
@@ -83,7 +83,35 @@ def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], 
         c.te_out_dim = te.out_dim
         c.te_global_context = int(te.global_context)
         c.te_use_tanh = int(te.use_tanh)
+    if unet is not None:  # UNET1D as RectifiedFlow.net (unet1d.py:255-268)
+        n = len(unet.channels)
+        if n > L.MAX_STAGES:
+            raise ValueError("too many UNET1D levels")
+        c.un_in_size = unet.in_size
+        c.un_out_size = unet.out_size or 0
+        c.un_n_levels = n
+        for i, ch in enumerate(unet.channels):
+            c.un_channels[i] = ch
+        for i, r in enumerate(list(unet.ratios)[:n - 1]):
+            c.un_ratios[i] = r
+        c.un_kernel_size = unet.kernel_size
+        c.un_time_channels = unet.time_channels
+        c.un_time_cond_in_channels = unet.time_cond_in_channels
+        c.un_time_cond_channels = unet.time_cond_channels
+        c.un_cond_channels = unet.cond_channels
+        c.un_n_attn_layers = unet.n_attn_layers
+        c.un_use_res_last = int(unet.use_res_last)
+        if model is None:  # the sampler-facing dimensions follow the net
+            c.n_channels = unet.in_size
+            c.cond_dim = unet.cond_channels
+            c.tcond_dim = unet.time_cond_in_channels
+            if seq_len is None:
+                raise ValueError("seq_len must be given for a UNET1D engine")
     return c
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
 
 
 class Engine:
@@ -102,9 +130,15 @@ class Engine:
                  max_steps: int = 50,
                  seq_len: Optional[int] = None,
                  max_samples: int = 524288,
-                 max_cache_size: int = 0):
+                 max_cache_size: int = 0,
+                 unet=None,
+                 unet_state: Optional[Dict[str, torch.Tensor]] = None,
+                 drop_value: Optional[float] = None):
         """``max_cache_size`` > 0 enables the streaming denoiser (what ``after_scripts/export.py:74-79`` binds to
-        LOCAL_ATTENTION_SIZE): one rolling KV history per ``cache_index`` in [0, max_steps)."""
+        LOCAL_ATTENTION_SIZE): one rolling KV history per ``cache_index`` in [0, max_steps).
+        ``unet`` / ``unet_state``: a ``config.UNetConfig`` + ``UNET1D.state_dict()`` make the conv denoiser
+        (after/diffusion/networks/unet1d.py) the engine's ``net`` instead of DenoiserV2: ``sample`` / ``model_forward`` then
+        run over it, and ``unet_forward`` is ``UNET1D.forward``."""
         self._lib = L.load()
         self._h = C.c_void_p()
         if precision not in L.PRECISIONS:
@@ -115,7 +149,10 @@ class Engine:
         self.ae_cfg = autoencoder
         self.cfg = _fill_config(model, autoencoder if autoencoder_state is not None else None, max_batch, max_steps,
                                 seq_len, max_samples, structure_state is not None, timbre_state is not None,
-                                max_cache_size)
+                                max_cache_size, unet if unet_state is not None else None)
+        if drop_value is not None:
+            self.cfg.drop_value = float(drop_value)
+        self.unet_cfg = unet
         L.check(self._lib.after_create(C.byref(self.cfg), device, C.byref(self._h)), None, "after_create")
         try:
             if denoiser_state is not None:
@@ -126,13 +163,20 @@ class Engine:
                 self._load(L.MODULE_STRUCTURE_ENCODER, structure_state)
             if timbre_state is not None:
                 self._load(L.MODULE_TIMBRE_ENCODER, timbre_state)
-            if any(s is not None for s in (denoiser_state, autoencoder_state, structure_state, timbre_state)):
+            if unet_state is not None:
+                if unet is None:
+                    raise ValueError("unet_state needs a UNetConfig (unet=)")
+                if denoiser_state is not None:
+                    raise ValueError("an engine carries one `net`: pass denoiser_state or unet_state, not both")
+                self._load(L.MODULE_UNET, unet_state)
+            if any(s is not None for s in (denoiser_state, autoencoder_state, structure_state, timbre_state, unet_state)):
                 L.check(self._lib.after_finalize_weights(self._h, L.PRECISIONS[precision]), self._h,
                         "after_finalize_weights")
         except Exception:
             self.close()
             raise
         self.has_denoiser = denoiser_state is not None
+        self.has_unet = unet_state is not None
         self.has_codec = autoencoder_state is not None
         self.has_structure = structure_state is not None
         self.has_timbre = timbre_state is not None
@@ -270,24 +314,63 @@ class Engine:
         return out
 
     def _check_cond(self, cond, time_cond, B, T):
+        if self.has_unet:
+            return self._check_cond_unet(cond, time_cond, B, T)
         if tuple(cond.shape) != (B, self.cfg.cond_dim):
             raise ValueError(f"cond must be ({B}, {self.cfg.cond_dim}), got {tuple(cond.shape)}")
         if tuple(time_cond.shape) != (B, self.cfg.tcond_dim, T):
             raise ValueError(f"time_cond must be ({B}, {self.cfg.tcond_dim}, {T}), got {tuple(time_cond.shape)}")
+
+    def _check_cond_unet(self, cond, time_cond, B, T):
+        u = self.unet_cfg
+        if u.cond_channels and (cond is None or tuple(cond.shape) != (B, u.cond_channels)):
+            raise ValueError(f"cond must be ({B}, {u.cond_channels})")
+        if u.time_cond_in_channels and (time_cond is None or tuple(time_cond.shape) != (B, u.time_cond_in_channels, T)):
+            raise ValueError(f"time_cond must be ({B}, {u.time_cond_in_channels}, {T})")
+
+    def _conds(self, cond, time_cond):
+        if self.has_unet:
+            u = self.unet_cfg
+            return self._opt(cond, "cond", u.cond_channels > 0), self._opt(time_cond, "time_cond", u.time_cond_in_channels > 0)
+        return self._dev(cond, "cond"), self._dev(time_cond, "time_cond")
+
+    def _opt(self, t, name, want: bool):
+        """Device tensor or None (a UNET1D without that condition takes no tensor for it)."""
+        if not want or t is None or t.numel() == 0:
+            return None
+        return self._dev(t, name)
+
+    def unet_forward(self, x, time, cond=None, time_cond=None):
+        """``UNET1D.forward(x, time=, time_cond=, cond=)`` (unet1d.py:376-429): (N, in_size, T) -> (N, out_size, T)."""
+        if not self.has_unet:
+            raise RuntimeError("this engine has no UNET1D weights")
+        u = self.unet_cfg
+        x = self._dev(x, "x")
+        N, _, T = x.shape
+        time = self._dev(time, "time").reshape(N, -1)[:, 0].contiguous()
+        cond = self._opt(cond, "cond", u.cond_channels > 0)
+        time_cond = self._opt(time_cond, "time_cond", u.time_cond_in_channels > 0)
+        self._check_cond_unet(cond, time_cond, N, T)
+        out = torch.empty(N, u.out_size or u.in_size, T, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(
+                self._lib.after_unet_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr() if cond is not None else None,
+                                             time_cond.data_ptr() if time_cond is not None else None, out.data_ptr(), N, T,
+                                             self._stream()), self._h, "after_unet_forward")
+        return out
 
     def model_forward(self, x, time, cond, time_cond, guidance_timbre, guidance_structure, cfg_variant=L.CFG_AUDIO,
                       clamp=0.01, cache_index: Optional[int] = None):
         x = self._dev(x, "x")
         B, _, T = x.shape
         time = self._dev(time, "time").reshape(B, -1)[:, 0].contiguous()
-        cond = self._dev(cond, "cond")
-        time_cond = self._dev(time_cond, "time_cond")
+        cond, time_cond = self._conds(cond, time_cond)
         self._check_cond(cond, time_cond, B, T)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             if cache_index is None:
                 L.check(
-                    self._lib.after_model_forward(self._h, x.data_ptr(), time.data_ptr(), cond.data_ptr(), time_cond.data_ptr(),
+                    self._lib.after_model_forward(self._h, x.data_ptr(), time.data_ptr(), _ptr(cond), _ptr(time_cond),
                                                   out.data_ptr(), B, T, float(guidance_timbre), float(guidance_structure),
                                                   int(cfg_variant), float(clamp), self._stream()), self._h,
                     "after_model_forward")
@@ -304,13 +387,12 @@ class Engine:
                clamp=0.01):
         x0 = self._dev(x0, "x0")
         B, _, T = x0.shape
-        cond = self._dev(cond, "cond")
-        time_cond = self._dev(time_cond, "time_cond")
+        cond, time_cond = self._conds(cond, time_cond)
         self._check_cond(cond, time_cond, B, T)
         out = torch.empty_like(x0)
         with torch.cuda.device(self.device):
             L.check(
-                self._lib.after_sample(self._h, x0.data_ptr(), cond.data_ptr(), time_cond.data_ptr(), out.data_ptr(), B, T,
+                self._lib.after_sample(self._h, x0.data_ptr(), _ptr(cond), _ptr(time_cond), out.data_ptr(), B, T,
                                        int(nb_steps), float(guidance_timbre), float(guidance_structure), int(cfg_variant),
                                        float(clamp), self._stream()), self._h, "after_sample")
         return out

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AFTER_B200_ABI_VERSION 2
+#define AFTER_B200_ABI_VERSION 3
 
 /* error codes */
 #define AFTER_OK 0
@@ -59,6 +59,7 @@ extern "C" {
 #define AFTER_MODULE_AUTOENCODER 1       /* emb_model                : AutoEncoder state_dict  */
 #define AFTER_MODULE_STRUCTURE_ENCODER 2 /* RectifiedFlow.encoder_time: Encoder1D state_dict   */
 #define AFTER_MODULE_TIMBRE_ENCODER 3    /* RectifiedFlow.encoder    : ECAPATDNN state_dict    */
+#define AFTER_MODULE_UNET 4              /* RectifiedFlow.net        : UNET1D state_dict (instead of DenoiserV2) */
 
 /* classifier-free-guidance row layouts */
 #define AFTER_CFG_AUDIO 0 /* (cond,tc)/(drop,tc)/(drop,drop), f = g_t/max(g_s,clamp)  model.py:730-759 */
@@ -120,6 +121,20 @@ typedef struct after_config {
   /* --- streaming (transformerv2.py:119-155; after_scripts/export.py:74-79 binds it to LOCAL_ATTENTION_SIZE) --- */
   int32_t max_cache_size; /* frames of key/value history per (layer, diffusion step, sequence); 0 = offline only.
                              One history per cache_index in [0, max_steps) and per sequence in [0, 3*max_batch). */
+  /* --- UNET1D conv denoiser (unet1d.py:255-268), the other `net` RectifiedFlow can bind; un_n_levels == 0 disables.
+   *     seq_len / max_batch / max_steps / drop_value above size and parameterise it as they do DenoiserV2. --- */
+  int32_t un_in_size;
+  int32_t un_out_size;                    /* 0: same as un_in_size */
+  int32_t un_n_levels;                    /* len(channels) */
+  int32_t un_channels[AFTER_MAX_STAGES];
+  int32_t un_ratios[AFTER_MAX_STAGES];    /* the reference's `ratios` (a leading 1 is prepended); un_n_levels - 1 entries used */
+  int32_t un_kernel_size;                 /* odd, <= 7 */
+  int32_t un_time_channels;               /* SPE dim */
+  int32_t un_time_cond_in_channels;
+  int32_t un_time_cond_channels;          /* 0: time_cond is concatenated to the input instead of embedded per scale */
+  int32_t un_cond_channels;               /* 0: no global condition */
+  int32_t un_n_attn_layers;
+  int32_t un_use_res_last;
 } after_config;
 
 typedef struct after_ctx* after_handle;
@@ -152,7 +167,15 @@ int after_finalize_weights(after_handle h, int precision);
 int after_denoiser_forward(after_handle h, const float* x, const float* time, const float* cond,
                            const float* time_cond, float* out, int N, int T, void* stream);
 
-/* RectifiedFlow.model_forward (model.py:721-761): one CFG-combined velocity evaluation.
+/* UNET1D.forward (unet1d.py:376-429): out = net(x, time=, time_cond=, cond=) for a handle that carries UNET1D weights
+ * (AFTER_MODULE_UNET).  x dev (N,in_size,T); time dev (N,); cond dev (N,cond_channels) or NULL when the net has no global
+ * condition; time_cond dev (N,time_cond_in_channels,T) or NULL when it has none; out dev (N,out_size,T).
+ * T must be a multiple of the product of the ratios. */
+int after_unet_forward(after_handle h, const float* x, const float* time, const float* cond, const float* time_cond,
+                       float* out, int N, int T, void* stream);
+
+/* RectifiedFlow.model_forward (model.py:721-761): one CFG-combined velocity evaluation.  Runs over whichever `net` the
+ * handle carries (DenoiserV2, or UNET1D when only AFTER_MODULE_UNET tensors were loaded); same for after_sample*.
  * x, out: dev (B,C,T); time: dev (B,); cond dev (B,zt); time_cond dev (B,zs,T). */
 int after_model_forward(after_handle h, const float* x, const float* time, const float* cond,
                         const float* time_cond, float* out, int B, int T, float guidance_timbre,

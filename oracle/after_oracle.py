@@ -182,23 +182,29 @@ CFG_MIDI = 1  # rows: (cond, tc) / (cond, drop) / (drop, drop); factor = g_s / m
 
 def model_forward(sd, cfg, x, time, cond, time_cond, guidance_timbre: float,
                   guidance_structure: float, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
-                  clamp: float = 0.01, cache: Optional[StreamCache] = None, cache_index: int = 0) -> Tensor:
+                  clamp: float = 0.01, cache: Optional[StreamCache] = None, cache_index: int = 0, net=None) -> Tensor:
     """3-way classifier-free-guidance evaluation; model.py:721-761 (audio variant) and
-    after_scripts/export_midi.py:322-360 (midi variant, clamp 0.1)."""
+    after_scripts/export_midi.py:322-360 (midi variant, clamp 0.1).  ``net(x, t, cond, time_cond)`` is the velocity
+    network (default: DenoiserV2 with ``sd`` / ``cfg``; ``unet_net(sd, cfg)`` gives the UNET1D one).  A condition the
+    network does not take is passed as None."""
     B = x.shape[0]
     idx = torch.arange(B).repeat(3)
-    drop_c = torch.full_like(cond, drop_value)
-    drop_t = torch.full_like(time_cond, drop_value)
+    drop_c = torch.full_like(cond, drop_value) if cond is not None else None
+    drop_t = torch.full_like(time_cond, drop_value) if time_cond is not None else None
+    cat = lambda parts: torch.cat(parts) if parts[0] is not None else None  # noqa: E731
     if cfg_variant == CFG_AUDIO:
-        conds = torch.cat([cond, drop_c, drop_c])
-        tconds = torch.cat([time_cond, time_cond, drop_t])
+        conds = cat([cond, drop_c, drop_c])
+        tconds = cat([time_cond, time_cond, drop_t])
         g_first, g_second = guidance_timbre, guidance_structure
     else:
-        conds = torch.cat([cond, cond, drop_c])
-        tconds = torch.cat([time_cond, drop_t, drop_t])
+        conds = cat([cond, cond, drop_c])
+        tconds = cat([time_cond, drop_t, drop_t])
         g_first, g_second = guidance_structure, guidance_timbre
     t = time.reshape(B, -1)[:, 0]
-    d = denoiser_forward(sd, cfg, x[idx], t[idx], conds, tconds, cache=cache, cache_index=cache_index)
+    if net is None:
+        d = denoiser_forward(sd, cfg, x[idx], t[idx], conds, tconds, cache=cache, cache_index=cache_index)
+    else:
+        d = net(x[idx], t[idx], conds, tconds)
     d_full, d_mid, d_none = d[:B], d[B:2 * B], d[2 * B:]
     total = 0.5 * (guidance_structure + guidance_timbre)
     factor = g_first / max(g_second, clamp)
@@ -208,7 +214,7 @@ def model_forward(sd, cfg, x, time, cond, time_cond, guidance_timbre: float,
 @torch.no_grad()
 def sample(sd, cfg, x0, cond, time_cond, nb_steps: int, guidance_timbre: float = 1.0,
            guidance_structure: float = 1.0, drop_value: float = -4.0, cfg_variant: int = CFG_AUDIO,
-           clamp: float = 0.01) -> Tensor:
+           clamp: float = 0.01, net=None) -> Tensor:
     """Fixed-step Euler integration of the velocity field on t_i = i / N; model.py:763-785."""
     x = x0
     B = x0.shape[0]
@@ -217,8 +223,13 @@ def sample(sd, cfg, x0, cond, time_cond, nb_steps: int, guidance_timbre: float =
     for t in ts:
         tt = t.to(x.dtype).reshape(1).repeat(B)
         x = x + model_forward(sd, cfg, x, tt, cond, time_cond, guidance_timbre,
-                              guidance_structure, drop_value, cfg_variant, clamp) * dt
+                              guidance_structure, drop_value, cfg_variant, clamp, net=net) * dt
     return x
+
+
+def unet_net(sd, cfg):
+    """The UNET1D velocity network as a ``net`` for ``model_forward`` / ``sample`` (RectifiedFlow binds either net)."""
+    return lambda x, t, cond, time_cond: unet1d_forward(sd, cfg, x, t, cond, time_cond)
 
 
 @torch.no_grad()

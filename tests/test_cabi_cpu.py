@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_build_info(lib):
     from after_b200 import _lib
-    assert lib.after_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.after_abi_version() == _lib.ABI_VERSION == 3
     assert b"sm_100a" in lib.after_build_info()
 
 
@@ -44,7 +44,7 @@ def test_config_struct_layout_matches_header(lib, tmp_path):
     from after_b200 import _lib
     src = tmp_path / "sz.c"
     fields = ["abi_version", "drop_value", "max_steps", "ae_multipliers", "ae_max_samples", "se_in_size", "se_use_tanh",
-              "max_cache_size"]
+              "max_cache_size", "un_in_size", "un_ratios", "un_use_res_last"]
     body = "".join(f'printf("%zu\\n", offsetof(after_config, {f}));' for f in fields)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "after_b200.h"\n'
                    f'int main(void){{printf("%zu\\n", sizeof(after_config));{body}return 0;}}\n')
