@@ -286,19 +286,23 @@ def _wn_conv(sd, prefix, x, stride=1, dilation=1, pad=None, causal=False):
     return F.conv1d(F.pad(x, pad), w, sd[prefix + ".bias"], stride=stride, dilation=dilation)
 
 
-def _conv_block(sd, prefix, x, dilation=1, groups=8):
-    """GroupNorm(min(C,8)) -> SnakeBeta -> conv; SimpleNetsStream.py:150-194."""
+def _conv_block(sd, prefix, x, dilation=1, groups=8, norm=None):
+    """GroupNorm(min(C,8)) -> SnakeBeta -> conv; SimpleNetsStream.py:150-194.  ``norm(key, x, groups, weight, bias)``
+    replaces the offline GroupNorm (the streaming oracle passes CachedGroupNorm's stream branch); a codec built with
+    ``use_norm = False`` has no gn tensors and skips the norm (SimpleNetsStream.py:165-167)."""
     C = x.shape[1]
-    y = F.group_norm(x, min(C, groups), sd[prefix + ".net.0.gn.weight"], sd[prefix + ".net.0.gn.bias"],
-                     eps=1e-5)
+    y = x
+    if (prefix + ".net.0.gn.weight") in sd:
+        w, b = sd[prefix + ".net.0.gn.weight"], sd[prefix + ".net.0.gn.bias"]
+        y = norm(prefix + ".net.0", x, min(C, groups), w, b) if norm is not None else F.group_norm(x, min(C, groups), w, b, eps=1e-5)
     y = snake_beta(y, sd[prefix + ".net.1.alpha"], sd[prefix + ".net.1.beta"])
     return _wn_conv(sd, prefix + ".net.2", y, dilation=dilation)
 
 
-def _resnet(sd, prefix, x, dilation=1, groups=8):
+def _resnet(sd, prefix, x, dilation=1, groups=8, norm=None):
     """block2(block1(x)) + skip(x); SimpleNetsStream.py:197-254."""
-    y = _conv_block(sd, prefix + ".net.branches.0.0", x, dilation, groups)
-    y = _conv_block(sd, prefix + ".net.branches.0.1", y, 1, 8)
+    y = _conv_block(sd, prefix + ".net.branches.0.0", x, dilation, groups, norm)
+    y = _conv_block(sd, prefix + ".net.branches.0.1", y, 1, 8, norm)
     skip_key = prefix + ".net.branches.1.weight_v"
     skip = _wn_conv(sd, prefix + ".net.branches.1", x) if skip_key in sd else x
     return y + skip
@@ -344,8 +348,8 @@ def ae_encode(sd: StateDict, cfg, audio: Tensor) -> Tensor:
     return _wn_conv(sd, f"encoder.net.{n + 2}", x)
 
 
-def ae_decode(sd: StateDict, cfg, z: Tensor) -> Tensor:
-    """``AutoEncoder.decode``; SimpleNetsStream.py:943-954, 552-651, 344-384, 51-70."""
+def ae_decode(sd: StateDict, cfg, z: Tensor, norm=None) -> Tensor:
+    """``AutoEncoder.decode``; SimpleNetsStream.py:943-954, 552-651, 344-384, 51-70.  ``norm``: see ``_conv_block``."""
     sd = _cast(sd, z.dtype)
     x = _wn_conv(sd, "decoder.net.0", z)
     nb = cfg.num_blocks
@@ -355,9 +359,9 @@ def ae_decode(sd: StateDict, cfg, z: Tensor) -> Tensor:
         w = fold_weight_norm(sd, f"{p}.net.1")  # (in, out, k): norm per *input* channel
         x = F.conv_transpose1d(x, w, sd[f"{p}.net.1.bias"], stride=f, padding=f // 2)
         for j in range(nb):
-            x = _resnet(sd, f"{p}.net.{2 + j}", x, cfg.dilations[j], cfg.resnet_groups)
-    x = _conv_block(sd, "decoder.synth.branches.0.net.0", x, 1, cfg.resnet_groups)
-    x = _conv_block(sd, "decoder.synth.branches.0.net.1", x, 1, 8)
+            x = _resnet(sd, f"{p}.net.{2 + j}", x, cfg.dilations[j], cfg.resnet_groups, norm)
+    x = _conv_block(sd, "decoder.synth.branches.0.net.0", x, 1, cfg.resnet_groups, norm)
+    x = _conv_block(sd, "decoder.synth.branches.0.net.1", x, 1, 8, norm)
     if cfg.use_loudness:
         half = x.shape[1] // 2
         x = x[:, :half] * torch.sigmoid(x[:, half:])
