@@ -82,6 +82,9 @@ class AfterConfig(C.Structure):
         ("un_cond_channels", C.c_int32),
         ("un_n_attn_layers", C.c_int32),
         ("un_use_res_last", C.c_int32),
+        ("stream_slots", C.c_int32),
+        ("stream_max_frames", C.c_int32),
+        ("stream_gn_frames", C.c_int32),
     ]
 
 
@@ -116,6 +119,10 @@ PROTOTYPES = {
                                       C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "after_ae_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "after_ae_decode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_ae_encode_stream": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "after_ae_decode_stream": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_structure_encode_stream": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_stream_reset": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "after_structure_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_timbre_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_generate": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float,

@@ -407,6 +407,46 @@ int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, 
   });
 }
 
+int after_ae_encode_stream(after_handle h, int slot, const float* audio, float* z, int B, int64_t samples, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
+    AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
+    BridgeScope bridge(h->bridge, stream);
+    h->codec.encode_stream(slot, audio, z, B, samples, h->bridge.work);
+  });
+}
+
+int after_ae_decode_stream(after_handle h, int slot, const float* z, float* audio, int B, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_codec, AFTER_ESTATE, "no autoencoder weights on this handle");
+    AFTER_REQUIRE(audio && z, AFTER_EINVAL, "null tensor pointer");
+    BridgeScope bridge(h->bridge, stream);
+    h->codec.decode_stream(slot, z, audio, B, T, h->bridge.work);
+  });
+}
+
+int after_structure_encode_stream(after_handle h, int slot, const float* z, float* time_cond, int B, int T, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_structure, AFTER_ESTATE, "no structure-encoder weights on this handle");
+    AFTER_REQUIRE(z && time_cond, AFTER_EINVAL, "null tensor pointer");
+    BridgeScope bridge(h->bridge, stream);
+    h->structure.forward_stream(slot, z, time_cond, B, T, h->bridge.work);
+  });
+}
+
+int after_stream_reset(after_handle h, int slot, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(h->have_codec || h->have_structure, AFTER_ESTATE, "no streaming sub-model on this handle");
+    BridgeScope bridge(h->bridge, stream);
+    if (h->have_codec) h->codec.reset_stream_slot(slot, h->bridge.work);
+    if (h->have_structure) h->structure.reset_stream_slot(slot, h->bridge.work);
+  });
+}
+
 int after_structure_encode(after_handle h, const float* z, float* time_cond, int B, int T, void* stream) {
   return guarded(h, [&] {
     require_ready(h);

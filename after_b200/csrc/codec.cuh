@@ -119,6 +119,7 @@ struct ConvLayer {
   int cin = 0, cout = 0;
   int in_phases = 1;   // input frames per GEMM row (stride of a strided conv)
   int out_phases = 1;  // output frames per GEMM row (stride of a transposed conv)
+  int sid = -1;        // streaming: index of this conv's cached-context state (-1: stateless, e.g. kernel size 1)
 };
 
 struct NormAct {
@@ -126,12 +127,14 @@ struct NormAct {
   int norm = NORM_NONE, act = ACT_NONE;
   float *gamma = nullptr, *beta = nullptr, *alpha = nullptr, *inv_beta = nullptr;  // GroupNorm affine, Snake
   float *mu = nullptr, *rs = nullptr, *be = nullptr;                              // folded BatchNorm
+  int gid = -1;  // streaming: index of this GroupNorm's statistics history (CachedGroupNorm stream branch)
 };
 
 struct ResBlock {
   NormAct a1, a2;
   ConvLayer c1, c2, skip;
   bool has_skip = false;
+  int rid = -1, delay = 0;  // streaming: residual-branch delay state (cached_conv AlignBranches)
 };
 
 // Shared machinery of the two conv nets.
@@ -271,6 +274,162 @@ struct ConvNet {
     graphs.init();
   }
 
+  // ---- streaming: cached_conv / CachedGroupNorm(stream=True) state ------------------------------------------------
+  // The reference's streaming export builds its convs under cc.use_cached_conv(True): every conv with padding (l, r)
+  // keeps the last l + r (+ stride delay) frames of its input and convolves [cache ; x] un-padded (CachedConv1d), the
+  // residual branches are delayed to match (AlignBranches), GroupNorm normalises over [previous P frames ; x]
+  // (SimpleNetsStream.py:134-144).  cached_conv (acids-ircam/cached_conv >= 2.5.0) is un-vendored: semantics restated in
+  // oracle/after_oracle_stream.py.  Here the cache IS the front of the conv's persistent operand buffer: the operand
+  // pass writes the new frames behind it, the tap-GEMM reads [cache ; new] through a TMA map whose taps are all
+  // non-negative shifts, and one roll kernel at the end of the call moves every conv's tail to its front.
+  struct StreamConv {
+    GemmWeight w;                       // same device weights as the offline layer, streaming tap table
+    int ns = 0, ns_al = 0, slab = 0;    // cached frames, rounded up to in_phases, frames per stream slab
+    int Cp = 0, in_phases = 1, t_scale = 1;  // t_scale: input frames of this conv per latent frame
+    bool tc = false;
+  };
+  struct StreamRes { int d = 0, C = 0, t_scale = 1; };
+  struct StreamGn { int groups = 1, C = 0, t_scale = 1, dir = 0; };  // dir: which frame counter (0 encoder, 1 decoder)
+  std::vector<StreamConv> sconv;
+  std::vector<StreamRes> sres;
+  std::vector<StreamGn> sgn;
+  struct Slot {
+    std::vector<ActOperand> op;   // per streaming conv
+    std::vector<float*> res;      // per delayed residual: [B][d][C]
+    std::vector<double*> hist;    // per GroupNorm: [B][cap][groups][2]
+    RollDesc* descs = nullptr;
+    long long* seen = nullptr;    // [2] latent frames consumed so far: encoder, decoder
+  };
+  std::vector<Slot> slots;
+  int stream_max_lat = 0;  // latent frames per streaming call the state is sized for
+  int gn_lat = 64;         // CachedGroupNorm padding_size in latent frames (the export's first call: 131072 samples)
+  float* xd_buf = nullptr; // delayed residual of the current block
+  struct StreamCtx { int slot = 0; int dir = 0; bool convs = false; };
+  const StreamCtx* sctx = nullptr;  // non-null while a streaming body runs
+
+  static int stride_delay(int r_pad, int cd, int stride) { return (stride - ((r_pad + cd) % stride)) % stride; }
+
+  // Register a conv for streaming.  (l, r): its padding; cd: cumulative delay in front of it (CachedConv1d.__init__).
+  // Returns the cumulative delay behind it.
+  int reg_conv(ConvLayer& L, int k, int dil, int l, int r, int stride, int cd, int t_scale) {
+    const int sd = stride_delay(r, cd, stride);
+    const int ns = l + r + sd;
+    const int out_cd = (r + sd + cd) / stride;
+    if (ns == 0) return out_cd;
+    AFTER_REQUIRE(L.in_phases == stride && L.out_phases == 1, AFTER_EINVAL, "streaming conv with an unexpected layout");
+    StreamConv c;
+    c.ns = ns; c.ns_al = ceil_div(ns, stride) * stride; c.in_phases = stride; c.t_scale = t_scale; c.Cp = L.w.Cin;
+    c.slab = c.ns_al + stream_max_lat * t_scale;
+    c.tc = tc_mode() && L.w.tc_ok;
+    c.w = L.w;
+    TapTable t;
+    t.ntaps = k;
+    const int off = c.ns_al - ns;
+    for (int i = 0; i < k; ++i) {
+      const int p = i * dil + off;
+      t.phase[0][i] = (int8_t)(p % stride);
+      t.shift[0][i] = (int16_t)(p / stride);
+    }
+    c.w.taps = t;
+    L.sid = (int)sconv.size();
+    sconv.push_back(c);
+    return out_cd;
+  }
+  int reg_res(ResBlock& r, int d, int C, int t_scale) {
+    r.delay = d;
+    if (d == 0) return -1;
+    AFTER_REQUIRE((size_t)d * C <= (size_t)256 * RD_MAX, AFTER_EINVAL, "residual delay state too large");
+    r.rid = (int)sres.size();
+    sres.push_back(StreamRes{d, C, t_scale});
+    return r.rid;
+  }
+  void reg_gn(NormAct& a, int t_scale, int dir) {
+    if (a.norm != NORM_GROUP) return;
+    AFTER_REQUIRE(256 % a.groups == 0, AFTER_EINVAL, "streaming GroupNorm needs a group count that divides 256");
+    a.gid = (int)sgn.size();
+    sgn.push_back(StreamGn{a.groups, a.C, t_scale, dir});
+  }
+  // ResnetBlock1d under cached_conv (SimpleNetsStream.py:197-254): block convs are built with cumulative_delay = 0, the
+  // skip branch is delayed by block1's delay d, the block adds d to the running delay.
+  int reg_res_block(ResBlock& r, int k, int dil, bool causal, int cd, int t_scale, int dir) {
+    const int p = (k - 1) * dil + 1;
+    const int l = k == 1 ? 0 : (causal ? p / 2 + (p - 1) / 2 : (p - 1) / 2), rr = k == 1 ? 0 : (causal ? 0 : p / 2);
+    const int d = reg_conv(r.c1, k, dil, l, rr, 1, 0, t_scale);
+    reg_res(r, d, r.c1.cin, t_scale);
+    reg_gn(r.a1, t_scale, dir);
+    reg_gn(r.a2, t_scale, dir);
+    return cd + d;
+  }
+  // allocate the per-slot state once everything is registered
+  void alloc_stream_state(int n_slots, int max_batch) {
+    slots.resize(n_slots);
+    for (Slot& s : slots) {
+      std::vector<RollDesc> descs;
+      for (const StreamConv& c : sconv) {
+        ActOperand o;
+        const size_t el = (size_t)c.slab * c.Cp * max_batch;
+        o.capacity = el;
+        o.bstride = (size_t)c.slab * c.Cp;
+        RollDesc d{};
+        if (c.tc) {
+          o.hi = arena->alloc<__nv_bfloat16>(el);
+          o.lo = arena->alloc<__nv_bfloat16>(el);
+          AFTER_CUDA_CHECK(cudaMemset(o.hi, 0, el * 2));
+          AFTER_CUDA_CHECK(cudaMemset(o.lo, 0, el * 2));
+          d.a = o.hi; d.b = nprod() > 1 ? (void*)o.lo : nullptr; d.elem_bytes = 2;
+        } else {
+          o.f32 = arena->alloc<float>(el);
+          AFTER_CUDA_CHECK(cudaMemset(o.f32, 0, el * 4));
+          d.a = o.f32; d.b = nullptr; d.elem_bytes = 4;
+        }
+        AFTER_REQUIRE(((size_t)c.Cp * d.elem_bytes) % 16 == 0, AFTER_EINVAL, "streaming conv operand rows must be 16-byte multiples");
+        d.ns = c.ns_al; d.Cp = c.Cp; d.slab = c.slab; d.t_scale = c.t_scale;
+        descs.push_back(d);
+        s.op.push_back(o);
+      }
+      for (const StreamRes& r : sres) {
+        float* p = arena->alloc<float>((size_t)max_batch * r.d * r.C);
+        AFTER_CUDA_CHECK(cudaMemset(p, 0, (size_t)max_batch * r.d * r.C * 4));
+        s.res.push_back(p);
+      }
+      for (const StreamGn& g : sgn) {
+        const size_t n = (size_t)max_batch * gn_cap(g) * g.groups * 2;
+        double* p = arena->alloc<double>(n);
+        AFTER_CUDA_CHECK(cudaMemset(p, 0, n * 8));
+        s.hist.push_back(p);
+      }
+      if (descs.empty()) descs.push_back(RollDesc{});
+      s.descs = arena->upload(descs);
+      if (!xd_buf) xd_buf = arena->alloc<float>(buf_elems);
+      s.seen = arena->alloc<long long>(2);
+      AFTER_CUDA_CHECK(cudaMemset(s.seen, 0, 16));
+    }
+  }
+  int gn_cap(const StreamGn& g) const { return (gn_lat + stream_max_lat + 8) * g.t_scale; }  // + 8: the decoder's z_buffer frames
+  // back to the state of a freshly constructed model: zero caches, zero GroupNorm history
+  void reset_stream(int slot, int max_batch, cudaStream_t st) {
+    Slot& s = slots.at(slot);
+    for (size_t i = 0; i < sconv.size(); ++i) {
+      const size_t el = (size_t)sconv[i].slab * sconv[i].Cp * max_batch;
+      if (s.op[i].hi) { AFTER_CUDA_CHECK(cudaMemsetAsync(s.op[i].hi, 0, el * 2, st)); AFTER_CUDA_CHECK(cudaMemsetAsync(s.op[i].lo, 0, el * 2, st)); }
+      if (s.op[i].f32) AFTER_CUDA_CHECK(cudaMemsetAsync(s.op[i].f32, 0, el * 4, st));
+    }
+    for (size_t i = 0; i < sres.size(); ++i) AFTER_CUDA_CHECK(cudaMemsetAsync(s.res[i], 0, (size_t)max_batch * sres[i].d * sres[i].C * 4, st));
+    for (size_t i = 0; i < sgn.size(); ++i)
+      AFTER_CUDA_CHECK(cudaMemsetAsync(s.hist[i], 0, (size_t)max_batch * gn_cap(sgn[i]) * sgn[i].groups * 2 * 8, st));
+    AFTER_CUDA_CHECK(cudaMemsetAsync(s.seen, 0, 16, st));
+  }
+  // end of a streaming call of `T_lat` latent frames: roll the conv caches, advance the frame counter
+  void finish_stream_call(int B, int T_lat, cudaStream_t st) {
+    const Slot& s = slots.at(sctx->slot);
+    if (sctx->convs && !sconv.empty()) {
+      launch_k(stream_roll_kernel, dim3((unsigned)sconv.size(), B), dim3(256), 0, st, (const RollDesc*)s.descs, T_lat, s.seen + sctx->dir);
+    } else {  // no conv state on this path (offline decoder with streaming GroupNorm): only the counter moves
+      launch_k(stream_advance_kernel, dim3(1), dim3(32), 0, st, T_lat, s.seen + sctx->dir);
+    }
+    AFTER_COUNT_LAUNCH();
+  }
+
   // ---- run-time helpers -------------------------------------------------------------------
   double* new_slot() {
     AFTER_REQUIRE(stat_next < stat_slots, AFTER_ESTATE, "statistics arena exhausted");
@@ -289,19 +448,42 @@ struct ConvNet {
                   "activation exceeds the codec workspace");
     ActParams p;
     p.norm = a.norm; p.act = a.act;
-    p.stats = xstats; p.groups = a.groups; p.gamma = a.gamma; p.beta = a.beta;
+    p.groups = a.groups; p.gamma = a.gamma; p.beta = a.beta;
     p.mu = a.mu; p.rs = a.rs; p.be = a.be; p.alpha = a.alpha; p.inv_beta = a.inv_beta;
+    if (a.norm == NORM_GROUP && sctx) {
+      // CachedGroupNorm stream branch: statistics over [previous P frames ; these T frames]
+      AFTER_REQUIRE(a.gid >= 0, AFTER_ESTATE, "GroupNorm was not registered for streaming");
+      const StreamGn& g = sgn[a.gid];
+      const Slot& sl = slots.at(sctx->slot);
+      const int P = gn_lat * g.t_scale;
+      AFTER_REQUIRE(T <= gn_cap(g) - P, AFTER_EINVAL, "streaming buffer longer than the state was sized for");
+      double* sw = new_slot();
+      launch_k(gn_window_kernel, dim3(ceil_div(P + T, GN_WIN_ENTRIES), B), dim3(256), 0, st, x, sl.hist[a.gid], sw, sl.seen + g.dir,
+               g.t_scale, P, gn_cap(g), T, C, g.groups);
+      AFTER_COUNT_LAUNCH();
+      xstats = sw;
+      p.stat_frames = P + T;
+    }
+    p.stats = xstats;
     if (a.norm == NORM_GROUP) AFTER_REQUIRE(xstats != nullptr, AFTER_ESTATE, "GroupNorm input has no statistics");
+    ActOperand* dst = &op;
+    int out_T = T, out_t0 = 0;
+    if (sctx && sctx->convs && consumer.sid >= 0) {  // streaming conv: the new frames go behind its cached context
+      const StreamConv& sc = sconv[consumer.sid];
+      AFTER_REQUIRE(T <= sc.slab - sc.ns_al, AFTER_EINVAL, "streaming buffer longer than the state was sized for");
+      dst = &slots.at(sctx->slot).op[consumer.sid];
+      out_T = sc.slab; out_t0 = sc.ns_al;
+    }
     OperandOut o;
-    if (tc_mode() && consumer.w.tc_ok) { o.hi = op.hi; o.lo = nprod() > 1 ? op.lo : nullptr; }
-    else o.f32 = op.f32;
+    if (tc_mode() && consumer.w.tc_ok) { o.hi = dst->hi; o.lo = nprod() > 1 ? dst->lo : nullptr; }
+    else o.f32 = dst->f32;
     const int fpb = std::max(1, 8192 / Cp);
     dim3 grid(ceil_div(T, fpb), B);
     const size_t smem = (size_t)5 * C * sizeof(float);
     const double el = (double)B * T;
     ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 * C + Cp * (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
-    if (C % 4 == 0 && Cp % 4 == 0) launch_k(act_operand_kernel<4>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb);
-    else launch_k(act_operand_kernel<1>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb);
+    if (C % 4 == 0 && Cp % 4 == 0) launch_k(act_operand_kernel<4>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
+    else launch_k(act_operand_kernel<1>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
     AFTER_COUNT_LAUNCH();
   }
 
@@ -313,11 +495,16 @@ struct ConvNet {
     e.out_f32 = out;
     e.ldo = L.w.N;
     e.res = res;
-    if (out_stats) {
+    if (out_stats && !sctx) {  // streaming GroupNorms take their statistics from the window kernel, not from the producer
       e.stats = out_stats;
       e.stat_groups = stat_groups;
       e.stat_cpg = L.cout / stat_groups;
       e.stat_cmod = L.out_phases > 1 ? L.cout : 0;
+    }
+    if (sctx && sctx->convs && L.sid >= 0) {
+      const StreamConv& sc = sconv[L.sid];
+      tap_gemm(slots.at(sctx->slot).op[L.sid], B, T_rows, L.in_phases, sc.w, e, precision, st, sc.ns_al / L.in_phases + T_rows);
+      return;
     }
     tap_gemm(op, B, T_rows, L.in_phases, L.w, e, precision, st);
   }
@@ -326,9 +513,14 @@ struct ConvNet {
   void res_block(const ResBlock& r, const float* x, const double* xstats, float* y1, float* out, double* out_stats,
                  int out_groups, int B, int T, cudaStream_t st) {
     const float* res = x;
+    if (sctx && sctx->convs && r.delay > 0) {  // AlignBranches: the skip branch sees x delayed by block1's conv delay
+      launch_k(res_delay_kernel, dim3(B), dim3(256), 0, st, x, slots.at(sctx->slot).res[r.rid], xd_buf, r.delay, T, r.c1.cin);
+      AFTER_COUNT_LAUNCH();
+      res = xd_buf;
+    }
     if (r.has_skip) {
       NormAct ident;
-      produce(x, ident, nullptr, r.skip, B, T, r.skip.cin, st);
+      produce(res, ident, nullptr, r.skip, B, T, r.skip.cin, st);
       conv(r.skip, B, T, out, nullptr, nullptr, 1, st);
       res = out;
     }
@@ -453,12 +645,56 @@ struct Codec : ConvNet {
       mxp = std::max(mxp, T * (size_t)std::max(dch[i], 64));
       if (i < n_stages) T *= c.ae_factors[n_stages - 1 - i];
     }
-    alloc_workspace(mx, mxp, c.max_batch, 2 * (n_stages * nb + 4) + 8);
+    alloc_workspace(mx, mxp, c.max_batch, 4 * (n_stages * nb + 4) + 16);
     io_audio = arena->alloc<float>((size_t)c.max_batch * c.ae_max_samples);
     io_z = arena->alloc<float>((size_t)c.max_batch * c.ae_z_channels * (c.ae_max_samples / ratio));
+
+    // ---- streaming export (after_scripts/export_autoencoder.py:16-153, 305-319: AE_notcausal = cached encoder + offline
+    // decoder over [z_buffer ; z] with overlap-add, CachedGroupNorm.stream = True in both)
+    if (c.stream_slots > 0) {
+      AFTER_REQUIRE(c.stream_slots <= 8, AFTER_EINVAL, "stream_slots must be <= 8");
+      n_fade = 4;  // export_autoencoder.py:57
+      gn_lat = c.stream_gn_frames > 0 ? c.stream_gn_frames : 64;
+      const int64_t max_lat = c.ae_max_samples / ratio - n_fade;
+      AFTER_REQUIRE(max_lat >= n_fade, AFTER_EINVAL, "ae_max_samples too small for the streaming decoder (needs n_fade + buffer frames)");
+      stream_max_lat = (int)std::min<int64_t>(c.stream_max_frames > 0 ? c.stream_max_frames : 64, max_lat);
+      int ts = ratio / M;  // frames at the PQMF rate per latent frame
+      int cd = reg_res_block(to_in, ks, 1, false, 0, ts, 0);
+      for (int i = 0; i < n_stages; ++i) {
+        Down& d = downs[i];
+        for (int j = 0; j < nb; ++j) cd = reg_res_block(d.res[j], ks, c.ae_dilations[j], false, cd, ts, 0);
+        cd = reg_conv(d.conv, 2 * d.f, 1, d.f - 1, d.f, d.f, cd, ts);  // Downsample1d: padding get_padding(2f, f) = (f-1, f)
+        AFTER_REQUIRE(ts % d.f == 0, AFTER_EINVAL, "codec ratio bookkeeping");
+        ts /= d.f;
+      }
+      cd = reg_conv(enc_out, 3, 1, 1, 1, 1, cd, ts);
+      enc_delay = cd;
+      ts = 1;
+      for (int i = 0; i < n_stages; ++i) {
+        ts *= ups[i].f;
+        for (int j = 0; j < nb; ++j) { reg_gn(ups[i].res[j].a1, ts, 1); reg_gn(ups[i].res[j].a2, ts, 1); }
+      }
+      reg_gn(out_a1, ts, 1);
+      reg_gn(out_a2, ts, 1);
+      alloc_stream_state(c.stream_slots, c.max_batch);
+      for (int sl = 0; sl < c.stream_slots; ++sl) {
+        const size_t nz = (size_t)c.max_batch * c.ae_z_channels * n_fade, no = (size_t)c.max_batch * ratio * n_fade;
+        float* zb = arena->alloc<float>(nz);
+        float* ob = arena->alloc<float>(no);
+        AFTER_CUDA_CHECK(cudaMemset(zb, 0, nz * 4));
+        AFTER_CUDA_CHECK(cudaMemset(ob, 0, no * 4));
+        z_buffer.push_back(zb);
+        out_buffer.push_back(ob);
+      }
+      zcat = arena->alloc<float>((size_t)c.max_batch * c.ae_z_channels * (stream_max_lat + n_fade));
+      ycat = arena->alloc<float>((size_t)c.max_batch * ratio * (stream_max_lat + n_fade));
+    }
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
     sd = nullptr;
   }
+  int n_fade = 4, enc_delay = 0;
+  std::vector<float*> z_buffer, out_buffer;  // per slot: AE_notcausal's z_buffer (B, Z, n_fade), out_buffer (B, 1, ratio n_fade)
+  float *zcat = nullptr, *ycat = nullptr;
 
   void destroy() { graphs.destroy(); }
 
@@ -574,13 +810,68 @@ struct Codec : ConvNet {
     graphs.run({1, B, T}, st, [&] { decode_body(io_z, io_audio, B, T, st); });
     AFTER_CUDA_CHECK(cudaMemcpyAsync(audio, io_audio, (size_t)B * T * ratio * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+
+  // ------------------------------------------------------------------ streaming export (export_stream.ts)
+  void check_stream(int slot, int B, int T_lat) {
+    AFTER_REQUIRE(!slots.empty(), AFTER_ESTATE, "this handle was created with stream_slots == 0 (no streaming codec state)");
+    AFTER_REQUIRE(slot >= 0 && slot < (int)slots.size(), AFTER_EINVAL, "stream slot out of range");
+    AFTER_REQUIRE(B >= 1 && B <= maxB, AFTER_EINVAL, "batch exceeds max_batch given at after_create");
+    AFTER_REQUIRE(T_lat >= 1 && T_lat <= stream_max_lat, AFTER_EINVAL, "buffer exceeds stream_max_frames given at after_create");
+  }
+  // AE_notcausal.encode on one buffer: offline PQMF of the buffer, cached-conv encoder, streaming GroupNorm
+  void encode_stream(int slot, const float* audio, float* z, int B, int64_t samples, cudaStream_t st) {
+    AFTER_REQUIRE(samples >= ratio && samples % ratio == 0, AFTER_EINVAL, "samples must be a positive multiple of the codec ratio");
+    const int T = (int)(samples / ratio);
+    check_stream(slot, B, T);
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_audio, audio, (size_t)B * samples * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    graphs.run({10 + slot, B, T}, st, [&] {
+      StreamCtx ctx{slot, 0, true};
+      sctx = &ctx;
+      struct Clear { const StreamCtx*& p; ~Clear() { p = nullptr; } } clear{sctx};
+      encode_body(io_audio, io_z, B, samples, st);
+      finish_stream_call(B, T, st);
+    });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(z, io_z, (size_t)B * cfg.ae_z_channels * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  // AE_notcausal.decode (export_autoencoder.py:128-153): decode [z_buffer ; z] offline (streaming GroupNorm), cross-fade the
+  // first n_fade frames with the tail kept from the previous call, keep the new tail, return the first T frames of audio
+  void decode_stream(int slot, const float* z, float* audio, int B, int T, cudaStream_t st) {
+    check_stream(slot, B, T);
+    AFTER_REQUIRE(T >= n_fade, AFTER_EINVAL, "the streaming decoder needs buffers of at least n_fade (4) latent frames");
+    const int Z = cfg.ae_z_channels, Tc = T + n_fade;
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_z, z, (size_t)B * Z * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    graphs.run({20 + slot, B, T}, st, [&] {
+      // zcat (B, Z, n_fade + T) = [z_buffer ; z]; z_buffer <- its last n_fade frames
+      AFTER_CUDA_CHECK(cudaMemcpy2DAsync(zcat, (size_t)Tc * 4, z_buffer[slot], (size_t)n_fade * 4, (size_t)n_fade * 4, (size_t)B * Z,
+                                         cudaMemcpyDeviceToDevice, st));
+      AFTER_CUDA_CHECK(cudaMemcpy2DAsync(zcat + n_fade, (size_t)Tc * 4, io_z, (size_t)T * 4, (size_t)T * 4, (size_t)B * Z,
+                                         cudaMemcpyDeviceToDevice, st));
+      AFTER_CUDA_CHECK(cudaMemcpy2DAsync(z_buffer[slot], (size_t)n_fade * 4, zcat + T, (size_t)Tc * 4, (size_t)n_fade * 4, (size_t)B * Z,
+                                         cudaMemcpyDeviceToDevice, st));
+      StreamCtx ctx{slot, 1, false};
+      sctx = &ctx;
+      struct Clear { const StreamCtx*& p; ~Clear() { p = nullptr; } } clear{sctx};
+      decode_body(zcat, ycat, B, Tc, st);
+      finish_stream_call(B, Tc, st);
+      const int n_out = T * ratio, nf = n_fade * ratio;
+      launch_k(overlap_add_kernel, dim3(ceil_div(n_out, 256), B), dim3(256), 0, st, (const float*)ycat, out_buffer[slot], io_audio, n_out, nf);
+      AFTER_COUNT_LAUNCH();
+    });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(audio, io_audio, (size_t)B * T * ratio * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  void reset_stream_slot(int slot, cudaStream_t st) {
+    check_stream(slot, 1, 1);
+    reset_stream(slot, maxB, st);
+    AFTER_CUDA_CHECK(cudaMemsetAsync(z_buffer[slot], 0, (size_t)maxB * cfg.ae_z_channels * n_fade * 4, st));
+    AFTER_CUDA_CHECK(cudaMemsetAsync(out_buffer[slot], 0, (size_t)maxB * ratio * n_fade * 4, st));
+  }
 };
 
 // ===========================================================================================
 // Encoder1D (structure encoder), all ratios == 1   (encoder.py:74-113, 116-237, 273-298)
 struct StructureEncoder : ConvNet {
   after_config cfg{};
-  struct Block { NormAct a1, a2; ConvLayer c1, c2; };
+  struct Block { NormAct a1, a2; ConvLayer c1, c2; int rid = -1, delay = 0; };
   std::vector<Block> blocks;   // n + 1 V2ConvBlock1D
   std::vector<ConvLayer> pools;  // n 1x1 convs
   std::vector<int> cins, couts;
@@ -611,16 +902,41 @@ struct StructureEncoder : ConvNet {
     make_block(blocks[n], "net." + std::to_string(n), couts[n - 1], c.se_kernel_size, c.se_causal != 0);
     maxT = c.seq_len;
     alloc_workspace((size_t)maxT * mxc, (size_t)maxT * std::max(mxc, 64), c.max_batch, 1);
+    // ---- Encoder1D.forward_stream (encoder.py:300-322) under cc.use_cached_conv(True) (after_scripts/export.py:14-17):
+    // V2ConvBlock1D chains conv1 -> conv2 delays and delays its identity branch by their sum (zero with causal padding)
+    if (c.stream_slots > 0) {
+      stream_max_lat = std::min(c.stream_max_frames > 0 ? c.stream_max_frames : 64, maxT);
+      const int k = c.se_kernel_size;
+      const bool causal = c.se_causal != 0;
+      const int l = k == 1 ? 0 : (causal ? k - 1 : (k - 1) / 2), r = k == 1 ? 0 : (causal ? 0 : k / 2);
+      for (Block& b : blocks) {
+        int cd = reg_conv(b.c1, k, 1, l, r, 1, 0, 1);
+        cd = reg_conv(b.c2, k, 1, l, r, 1, cd, 1);
+        b.delay = cd;
+        if (cd > 0) {
+          AFTER_REQUIRE((size_t)cd * b.c1.cin <= (size_t)256 * RD_MAX, AFTER_EINVAL, "residual delay state too large");
+          b.rid = (int)sres.size();
+          sres.push_back(StreamRes{cd, b.c1.cin, 1});
+        }
+      }
+      alloc_stream_state(c.stream_slots, c.max_batch);
+    }
     AFTER_CUDA_CHECK(cudaDeviceSynchronize());
     sd = nullptr;
   }
 
   // x + conv(SiLU(BN(conv(SiLU(BN(x))))))   (encoder.py:25-71, dropout off)
   void run_block(const Block& b, const float* x, float* y1, float* out, int B, int T, cudaStream_t st) {
+    const float* res = x;
+    if (sctx && b.delay > 0) {
+      launch_k(res_delay_kernel, dim3(B), dim3(256), 0, st, x, slots.at(sctx->slot).res[b.rid], xd_buf, b.delay, T, b.c1.cin);
+      AFTER_COUNT_LAUNCH();
+      res = xd_buf;
+    }
     produce(x, b.a1, nullptr, b.c1, B, T, b.c1.cin, st);
     conv(b.c1, B, T, y1, nullptr, nullptr, 1, st);
     produce(y1, b.a2, nullptr, b.c2, B, T, b.c2.cin, st);
-    conv(b.c2, B, T, out, x, nullptr, 1, st);
+    conv(b.c2, B, T, out, res, nullptr, 1, st);
   }
 
   void forward_body(const float* z, float* out, int B, int T, cudaStream_t st) {
@@ -652,6 +968,22 @@ struct StructureEncoder : ConvNet {
     AFTER_REQUIRE(B >= 1 && B <= maxB, AFTER_EINVAL, "batch exceeds max_batch given at after_create");
     AFTER_REQUIRE(T >= 1 && T <= maxT, AFTER_EINVAL, "T exceeds seq_len given at after_create");
     forward_body(z, out, B, T, st);
+  }
+  // Encoder1D.forward_stream: one buffer of T latent frames against the cached left context of every conv
+  void forward_stream(int slot, const float* z, float* out, int B, int T, cudaStream_t st) {
+    AFTER_REQUIRE(!slots.empty(), AFTER_ESTATE, "this handle was created with stream_slots == 0 (no streaming state)");
+    AFTER_REQUIRE(slot >= 0 && slot < (int)slots.size(), AFTER_EINVAL, "stream slot out of range");
+    AFTER_REQUIRE(B >= 1 && B <= maxB, AFTER_EINVAL, "batch exceeds max_batch given at after_create");
+    AFTER_REQUIRE(T >= 1 && T <= stream_max_lat, AFTER_EINVAL, "buffer exceeds stream_max_frames given at after_create");
+    StreamCtx ctx{slot, 0, true};
+    sctx = &ctx;
+    struct Clear { const StreamCtx*& p; ~Clear() { p = nullptr; } } clear{sctx};
+    forward_body(z, out, B, T, st);
+    finish_stream_call(B, T, st);
+  }
+  void reset_stream_slot(int slot, cudaStream_t st) {
+    AFTER_REQUIRE(slot >= 0 && slot < (int)slots.size(), AFTER_EINVAL, "stream slot out of range");
+    reset_stream(slot, maxB, st);
   }
   void destroy() { graphs.destroy(); }
 };

@@ -16,6 +16,7 @@ struct ActParams {
   //             (SimpleNetsStream.py:95-147 offline branch; statistics come from the producer's epilogue)
   const double* stats = nullptr;  // [B][groups][2] = sum, sum of squares
   int groups = 1;
+  int stat_frames = 0;            // frames the statistics cover (0: the T frames of this call; streaming: pad + T)
   const float* gamma = nullptr;   // [C]
   const float* beta = nullptr;    // [C]
   // NORM_AFFINE: y = (x - mu[c]) * rs[c] + be[c]   (eval-mode BatchNorm, encoder.py:39-48; folded at load)
@@ -56,7 +57,10 @@ __device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
 // C % 4 == 0 is required for the vector path (C4 = C / 4 float4 per frame); a scalar variant handles the rest.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int Cp, int frames_per_block) {
+act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int Cp, int frames_per_block,
+                   int out_T, int out_t0) {
+  // out_T / out_t0: the output holds out_T frames per stream and this call's frames start at out_t0 (offline: T and 0;
+  // streaming: the conv's persistent operand, whose first frames are the cached left context)
   pdl_wait();
   pdl_trigger();
   // Cp >= C: output channels [C, Cp) are written as zeros (operands of the few 16/32-channel layers are padded to the
@@ -73,7 +77,7 @@ act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int
     if (p.norm == NORM_GROUP) {
       const int cpg = C / p.groups;
       const int g = c / cpg;
-      const double n = (double)cpg * (double)T;
+      const double n = (double)cpg * (double)(p.stat_frames > 0 ? p.stat_frames : T);
       const double s = p.stats[((size_t)b * p.groups + g) * 2];
       const double q = p.stats[((size_t)b * p.groups + g) * 2 + 1];
       const double mean = s / n;
@@ -97,7 +101,7 @@ act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int f = i / per_frame;
     const int c = (i - f * per_frame) * VEC;
-    const size_t off = ((size_t)b * T + t0 + f) * Cp + c;
+    const size_t off = ((size_t)b * out_T + out_t0 + t0 + f) * Cp + c;
     float v[VEC];
     if (c < C) {
       const size_t in_off = ((size_t)b * T + t0 + f) * C + c;
@@ -279,6 +283,163 @@ pqmf_synthesis_kernel(const float* __restrict__ u, const float* __restrict__ wT,
     const int t = t0 + fg * 8 + f;
     if (t < T) audio[(size_t)b * T * M + (size_t)t * M + (M - 1 - m)] = acc[f] * (float)M;
   }
+}
+
+// -------------------------------------------------------------------------------------------
+// Streaming kernels (cached_conv / CachedGroupNorm stream branch, see codec.cuh "streaming")
+// -------------------------------------------------------------------------------------------
+// CachedGroupNorm stream branch (SimpleNetsStream.py:134-144): statistics over [pad ; x], pad = the previous P frames
+// (zeros before the start).  Per-frame per-group {sum, sumsq} of every frame seen live in a ring of cap = P + Tmax
+// entries per stream; entry of absolute frame a is at a % cap.  `seen` (device): absolute index of this call's first
+// frame = frames_seen_lat * scale.  The window [seen - P, seen + T) is reduced into stats[b][g] (pre-zeroed, fp64
+// atomics); entries of the new frames are computed from x and stored, older ones are read back.
+// grid = (ceil((P + T) / GN_WIN_ENTRIES), B), 256 threads, groups | 256.
+constexpr int GN_WIN_ENTRIES = 256;
+__global__ void __launch_bounds__(256)
+gn_window_kernel(const float* __restrict__ x, double* __restrict__ hist, double* __restrict__ stats,
+                 const long long* __restrict__ seen_lat, int scale, int P, int cap, int T, int C, int groups) {
+  __shared__ double red[256][2];
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const int g = threadIdx.x % groups;
+  const int epi = 256 / groups;  // entries per iteration
+  const long long seen = seen_lat[0] * (long long)scale;
+  double s = 0.0, q = 0.0;
+  const int w0 = blockIdx.x * GN_WIN_ENTRIES;
+  for (int w = w0 + threadIdx.x / groups; w < min(w0 + GN_WIN_ENTRIES, P + T); w += epi) {
+    const long long a = seen - P + w;  // absolute frame
+    if (a < 0) continue;               // before the start: zeros
+    double* e = hist + (((size_t)b * cap + (size_t)(a % cap)) * groups + g) * 2;
+    if (w < P) {
+      s += e[0]; q += e[1];
+    } else {
+      const float* xp = x + ((size_t)b * T + (w - P)) * C + g * cpg;
+      float fs = 0.f, fq = 0.f;
+      for (int c = 0; c < cpg; ++c) { const float v = xp[c]; fs += v; fq = fmaf(v, v, fq); }
+      e[0] = (double)fs; e[1] = (double)fq;
+      s += (double)fs; q += (double)fq;
+    }
+  }
+  red[threadIdx.x][0] = s; red[threadIdx.x][1] = q;
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double ts = 0.0, tq = 0.0;
+    for (int i = threadIdx.x; i < 256; i += groups) { ts += red[i][0]; tq += red[i][1]; }
+    double* d = stats + ((size_t)b * groups + threadIdx.x) * 2;
+    atomicAdd(d, ts);
+    atomicAdd(d + 1, tq);
+  }
+}
+
+// AlignBranches delay of a residual branch (cached_conv): xd[t] = X[t - d] over the stream X; state = last d frames.
+// grid = (B), 256 threads; d * C <= 256 * RD_MAX.
+constexpr int RD_MAX = 32;
+__global__ void __launch_bounds__(256)
+res_delay_kernel(const float* __restrict__ x, float* __restrict__ state, float* __restrict__ xd, int d, int T, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x;
+  const float* xb = x + (size_t)b * T * C;
+  float* sb = state + (size_t)b * d * C;
+  float* ob = xd + (size_t)b * T * C;
+  for (int i = threadIdx.x; i < T * C; i += 256) {
+    const int t = i / C;
+    ob[i] = t < d ? sb[i] : xb[i - d * C];
+  }
+  // new state = last d frames of [state ; x]: read everything this thread will write before anyone writes
+  float keep[RD_MAX];
+#pragma unroll
+  for (int j = 0; j < RD_MAX; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < d * C) {
+      const int src = i + T * C;  // index into [state ; x]
+      keep[j] = src < d * C ? sb[src] : xb[src - d * C];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RD_MAX; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < d * C) sb[i] = keep[j];
+  }
+}
+
+// End of a streaming call: every cached conv keeps the last `ns` frames of its operand in front of the next call's
+// frames (CachedPadding1d): slab[0, ns) <- slab[T, T + ns) for all layers at once.  One block per (layer, stream);
+// the copy moves data to lower addresses, chunk by chunk in ascending order with a barrier between a chunk's reads and
+// writes, so overlapping source / destination ranges (ns > T) are safe.  Block (0, 0) also advances the frame counter.
+struct RollDesc {
+  void* a;        // bf16 hi or fp32 slab base
+  void* b;        // bf16 lo slab base or null
+  int elem_bytes; // 2 | 4
+  int ns;         // frames kept (aligned count)
+  int Cp;         // channels per frame
+  int slab;       // frames per stream slab
+  int t_scale;    // frames of this layer's input per latent frame
+};
+__global__ void __launch_bounds__(256)
+stream_roll_kernel(const RollDesc* __restrict__ descs, int T_lat, long long* __restrict__ seen_lat) {
+  pdl_wait();
+  pdl_trigger();
+  const RollDesc d = descs[blockIdx.x];
+  const int b = blockIdx.y;
+  if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) seen_lat[0] += T_lat;
+  const int T = T_lat * d.t_scale;
+  const size_t row = (size_t)d.Cp * d.elem_bytes / 16;  // uint4 per frame (Cp * elem_bytes is a multiple of 16)
+  const size_t n = (size_t)d.ns * row, shift = (size_t)T * row;
+  for (int arr = 0; arr < 2; ++arr) {
+    uint4* base = reinterpret_cast<uint4*>(arr == 0 ? d.a : d.b);
+    if (!base) continue;
+    base += (size_t)b * d.slab * row;
+    for (size_t c0 = 0; c0 < n; c0 += 256 * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t i = c0 + threadIdx.x + 256 * j;
+        if (i < n) v[j] = base[i + shift];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t i = c0 + threadIdx.x + 256 * j;
+        if (i < n) base[i] = v[j];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void stream_advance_kernel(int T_lat, long long* __restrict__ seen_lat) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) seen_lat[0] += T_lat;
+}
+
+// AE_notcausal.decode (export_autoencoder.py:128-153), audio side: y (B, (T + nf) * r) decoded from [z_buffer ; z];
+//   y[:nf r] <- (1 - alpha) out_buffer + alpha y[:nf r], alpha = linspace(0, 1, nf r); out_buffer <- y[-nf r:];
+//   out (B, T r) <- y[:-nf r]
+__global__ void __launch_bounds__(256)
+overlap_add_kernel(const float* __restrict__ y, float* __restrict__ out_buffer, float* __restrict__ out, int n_out, int n_fade) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float* yb = y + (size_t)b * (n_out + n_fade);
+  float* ob = out_buffer + (size_t)b * n_fade;
+  // requires n_out >= n_fade (host checks): thread i < n_fade is the only reader and the only writer of out_buffer[i]
+  if (i < n_out) {
+    float v = yb[i];
+    if (i < n_fade) {
+      // torch.linspace(0, 1, n_fade)[i] the way ATen fills it (symmetric halves)
+      const float step = 1.0f / (float)(n_fade - 1);
+      const float alpha = i < n_fade / 2 ? step * (float)i : 1.0f - step * (float)(n_fade - 1 - i);
+      v = (1.0f - alpha) * ob[i] + alpha * v;
+    }
+    out[(size_t)b * n_out + i] = v;
+  }
+  if (i < n_fade) ob[i] = yb[n_out + i];  // last n_fade samples of y: beyond the faded head because n_out >= n_fade
 }
 
 // tanh epilogue of the structure encoder when use_tanh is set (encoder.py:296-297)

@@ -247,13 +247,13 @@ struct Denoiser {
     if (K % 16 == 0 && N % 4 == 0 && !gelu) {
       GemmEpi e; e.out_f32 = Cout; e.ldo = N; e.bias = bias;
       dim3 grid(ceil_div(N, SG_BN), ceil_div(M, SG_BM), 1);
-      tap_gemm_simt_kernel<<<grid, 256, 0, st>>>(A, W, e, tt, M, 1, K, N);
+      tap_gemm_simt_kernel<<<grid, 256, 0, st>>>(A, W, e, tt, M, 1, K, N, M, (size_t)0);
       AFTER_CUDA_CHECK(cudaGetLastError());
       AFTER_COUNT_LAUNCH();
       return;
     }
     const size_t total = (size_t)M * N;
-    tap_gemm_naive_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, W, bias, nullptr, Cout, tt, 1, M, 1, K, N, gelu);
+    tap_gemm_naive_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, W, bias, nullptr, Cout, tt, 1, M, 1, K, N, gelu, M, (size_t)0);
     AFTER_CUDA_CHECK(cudaGetLastError());
     AFTER_COUNT_LAUNCH();
   }

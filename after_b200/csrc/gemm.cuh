@@ -154,7 +154,9 @@ constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 
 __global__ void __launch_bounds__(256)
 tap_gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ W, GemmEpi epi, TapTable taps, int T, int P,
-                     int Cin, int N) {
+                     int Cin, int N, int Tin, size_t a_bstride) {
+  // Tin: input rows per stream (offline: T; a streaming conv reads [cached context ; new frames]); a_bstride: elements
+  // between the streams of A
   __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
   __shared__ __align__(16) float Ws[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
@@ -178,8 +180,8 @@ tap_gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ W, G
 
   for (int tap = 0; tap < taps.ntaps; ++tap) {
     const int tt = t0 + lrow + taps.shift[oph][tap];
-    const bool a_ok = tt >= 0 && tt < T;
-    const float* Ap = A + (((size_t)b * T + (a_ok ? tt : 0)) * P + taps.phase[oph][tap]) * Cin + lk;
+    const bool a_ok = tt >= 0 && tt < Tin;
+    const float* Ap = A + (size_t)b * a_bstride + ((size_t)(a_ok ? tt : 0) * P + taps.phase[oph][tap]) * Cin + lk;
     for (int c0 = 0; c0 < Cin; c0 += SG_BK) {
       float4 ra = a_ok ? *reinterpret_cast<const float4*>(Ap + c0) : make_float4(0, 0, 0, 0);
       float4 rw = w_ok ? *reinterpret_cast<const float4*>(Wp + (size_t)tap * Cin + c0) : make_float4(0, 0, 0, 0);
@@ -218,7 +220,7 @@ tap_gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ W, G
 __global__ void tap_gemm_naive_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                       const float* __restrict__ bias, const float* __restrict__ res,
                                       float* __restrict__ out, TapTable taps, int B, int T, int P, int Cin, int N,
-                                      int gelu) {
+                                      int gelu, int Tin, size_t a_bstride) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * T * N) return;
   const int n = (int)(idx % N);
@@ -229,8 +231,8 @@ __global__ void tap_gemm_naive_kernel(const float* __restrict__ A, const float* 
   float acc = 0.f;
   for (int tap = 0; tap < taps.ntaps; ++tap) {
     const int tt = t + taps.shift[oph][tap];
-    if (tt < 0 || tt >= T) continue;
-    const float* a = A + (((size_t)b * T + tt) * P + taps.phase[oph][tap]) * Cin;
+    if (tt < 0 || tt >= Tin) continue;
+    const float* a = A + (size_t)b * a_bstride + ((size_t)tt * P + taps.phase[oph][tap]) * Cin;
     const float* w = W + (size_t)n * K + (size_t)tap * Cin;
     for (int c = 0; c < Cin; ++c) acc = fmaf(a[c], w[c], acc);
   }

@@ -43,10 +43,11 @@ inline CUtensorMap make_tmap_weight(const void* ptr, int64_t rows, int64_t cols,
 
 // Activations: 4-D bf16 (C, P, T, B) with C fastest; box (64, 1, 128, 1).  Frames outside [0, T) are zero-filled
 // by the TMA unit, which is exactly the zero padding of the convolutions.
-inline CUtensorMap make_tmap_act(const void* ptr, int C, int P, int T, int B) {
+// bstride: elements between streams (0: densely packed, C * P * T).
+inline CUtensorMap make_tmap_act(const void* ptr, int C, int P, int T, int B, size_t bstride = 0) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * P * 2, (cuuint64_t)C * P * T * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * P * 2, (cuuint64_t)(bstride ? bstride : (size_t)C * P * T) * 2};
   cuuint32_t box[4] = {(cuuint32_t)tc::BK, 1, (cuuint32_t)tc::BM, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
@@ -99,14 +100,16 @@ struct ActOperand {
   size_t capacity = 0;  // elements
   struct Maps { CUtensorMap hi, lo; };
   std::map<std::tuple<int, int, int, int>, Maps> cache;
+  size_t bstride = 0;  // elements between streams (0: densely packed); set once for a streaming conv's persistent operand
   const Maps& maps(int C, int P, int T, int B) {
     auto key = std::make_tuple(C, P, T, B);
     auto it = cache.find(key);
     if (it == cache.end()) {
-      AFTER_REQUIRE((size_t)C * P * T * B <= capacity, AFTER_EINVAL, "activation view exceeds the operand buffer");
+      const size_t per = bstride ? bstride : (size_t)C * P * T;
+      AFTER_REQUIRE((size_t)C * P * T <= per && per * B <= capacity, AFTER_EINVAL, "activation view exceeds the operand buffer");
       Maps m;
-      m.hi = make_tmap_act(hi, C, P, T, B);
-      m.lo = make_tmap_act(lo ? lo : hi, C, P, T, B);
+      m.hi = make_tmap_act(hi, C, P, T, B, bstride);
+      m.lo = make_tmap_act(lo ? lo : hi, C, P, T, B, bstride);
       it = cache.emplace(key, m).first;
     }
     return it->second;
@@ -334,8 +337,12 @@ void gn_stats_launch(const float* x, double* stats, int B, int T, int C, int gro
 
 // Dispatch.  `precision` is the handle's arithmetic mode.  A: the operand (B, T, P, Cin).  The output is
 // (B, T, N) rows of epi.ldo floats.
+// T_in: input rows per stream when they differ from the T output rows (a streaming conv reads its cached left context
+// in front of the new frames; 0 = T); the operand's stream stride is A.bstride.
 inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, GemmEpi epi, int precision,
-                     cudaStream_t st) {
+                     cudaStream_t st, int T_in = 0) {
+  if (T_in <= 0) T_in = T;
+  const size_t a_bstride = A.bstride ? A.bstride : (size_t)T_in * P * W.Cin;
   const bool tc_mode = precision != AFTER_PRECISION_FP32_SIMT;
   epi.bias = W.bias;
   {
@@ -351,7 +358,7 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
   if (tc_mode && W.tc_ok) {
     AFTER_REQUIRE(A.hi != nullptr, AFTER_ESTATE, "operand has no bf16 copy");
     const int nprod = precision == AFTER_PRECISION_BF16 ? 1 : 3;
-    const ActOperand::Maps& am = A.maps(W.Cin, P, T, B);
+    const ActOperand::Maps& am = A.maps(W.Cin, P, T_in, B);
     const bool flavour_ok = (!epi.rope || (!epi.bias && !epi.res && !epi.gelu && !epi.stats)) &&
                             (!epi.gelu || (!epi.res && !epi.stats)) && (!epi.stats || epi.stat_cpg % 8 == 0);
     if (W.tc2_ok && use_pair_kernel() && flavour_ok) {
@@ -380,7 +387,7 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
                        (W.taps.n_per_phase == 0 || W.taps.n_per_phase % SG_BN == 0);
   if (simt_ok) {
     dim3 grid(ceil_div(W.N, SG_BN), ceil_div(T, SG_BM), B);
-    tap_gemm_simt_kernel<<<grid, 256, 0, st>>>(A.f32, W.w, epi, W.taps, T, P, W.Cin, W.N);
+    tap_gemm_simt_kernel<<<grid, 256, 0, st>>>(A.f32, W.w, epi, W.taps, T, P, W.Cin, W.N, T_in, a_bstride);
     AFTER_CUDA_CHECK(cudaGetLastError());
     AFTER_COUNT_LAUNCH();
     return;
@@ -389,7 +396,7 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
                 "naive tap-GEMM supports fp32 output only");
   const size_t total = (size_t)B * T * W.N;
   tap_gemm_naive_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A.f32, W.w, W.bias, epi.res, epi.out_f32, W.taps,
-                                                                         B, T, P, W.Cin, W.N, epi.gelu);
+                                                                         B, T, P, W.Cin, W.N, epi.gelu, T_in, a_bstride);
   AFTER_CUDA_CHECK(cudaGetLastError());
   AFTER_COUNT_LAUNCH();
   if (epi.stats) {

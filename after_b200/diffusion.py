@@ -76,8 +76,13 @@ class Encoder1D:
     def forward(self, z):
         return self.engine.structure_encode(z)
 
-    # same arithmetic in the reference (encoder.py:300-322); its cached-conv state across calls is not carried here
-    forward_stream = forward
+    def forward_stream(self, z, slot: int = 0):
+        """encoder.py:300-322 under ``cc.use_cached_conv(True)`` (after_scripts/export.py:14-17): every conv carries its left
+        context across calls.  Needs an engine created with ``stream_slots > 0``; an offline engine has no such state and,
+        like the reference module built without cached convs, processes the buffer on its own."""
+        if self.engine.stream_slots > 0:
+            return self.engine.structure_encode_stream(slot, z)
+        return self.engine.structure_encode(z)
 
     def eval(self):
         return self

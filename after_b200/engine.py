@@ -16,10 +16,14 @@ from .config import AutoEncoderConfig, DenoiserConfig, EcapaConfig, Encoder1DCon
 
 def _fill_config(model: Optional[ModelConfig], ae: Optional[AutoEncoderConfig], max_batch: int, max_steps: int,
                  seq_len: Optional[int], max_samples: int, use_structure: bool, use_timbre: bool = False,
-                 max_cache_size: int = 0, unet=None) -> L.AfterConfig:
+                 max_cache_size: int = 0, unet=None, stream_slots: int = 0, stream_max_frames: int = 0,
+                 stream_gn_frames: int = 0) -> L.AfterConfig:
     c = L.AfterConfig()
     c.abi_version = L.ABI_VERSION
     c.max_cache_size = max_cache_size
+    c.stream_slots = stream_slots
+    c.stream_max_frames = stream_max_frames
+    c.stream_gn_frames = stream_gn_frames
     d: DenoiserConfig = model.denoiser if model is not None else DenoiserConfig()
     c.n_channels = d.n_channels
     c.seq_len = seq_len if seq_len is not None else d.seq_len
@@ -133,12 +137,20 @@ class Engine:
                  max_cache_size: int = 0,
                  unet=None,
                  unet_state: Optional[Dict[str, torch.Tensor]] = None,
-                 drop_value: Optional[float] = None):
+                 drop_value: Optional[float] = None,
+                 stream_slots: int = 0,
+                 stream_max_frames: int = 0,
+                 stream_gn_frames: int = 0):
         """``max_cache_size`` > 0 enables the streaming denoiser (what ``after_scripts/export.py:74-79`` binds to
         LOCAL_ATTENTION_SIZE): one rolling KV history per ``cache_index`` in [0, max_steps).
         ``unet`` / ``unet_state``: a ``config.UNetConfig`` + ``UNET1D.state_dict()`` make the conv denoiser
         (after/diffusion/networks/unet1d.py) the engine's ``net`` instead of DenoiserV2: ``sample`` / ``model_forward`` then
-        run over it, and ``unet_forward`` is ``UNET1D.forward``."""
+        run over it, and ``unet_forward`` is ``UNET1D.forward``.
+        ``stream_slots`` > 0 adds that many independent streaming states to the codec and the structure encoder -- what the
+        exported ``export_stream.ts`` / ``Encoder1D.forward_stream`` keep in cached convolutions and CachedGroupNorm
+        (the exported Streamer holds two codec copies: slot 0 = structure, slot 1 = timbre); ``stream_max_frames`` = latent
+        frames per streaming call the state is sized for (default 64), ``stream_gn_frames`` = CachedGroupNorm's padding in
+        latent frames (default 64 = the 131072-sample first call of export_autoencoder.py)."""
         self._lib = L.load()
         self._h = C.c_void_p()
         if precision not in L.PRECISIONS:
@@ -149,7 +161,8 @@ class Engine:
         self.ae_cfg = autoencoder
         self.cfg = _fill_config(model, autoencoder if autoencoder_state is not None else None, max_batch, max_steps,
                                 seq_len, max_samples, structure_state is not None, timbre_state is not None,
-                                max_cache_size, unet if unet_state is not None else None)
+                                max_cache_size, unet if unet_state is not None else None, stream_slots, stream_max_frames,
+                                stream_gn_frames)
         if drop_value is not None:
             self.cfg.drop_value = float(drop_value)
         self.unet_cfg = unet
@@ -438,6 +451,50 @@ class Engine:
             L.check(self._lib.after_ae_decode(self._h, z.data_ptr(), audio.data_ptr(), B, T, self._stream()), self._h,
                     "after_ae_decode")
         return audio
+
+    # ---- streaming codec / structure encoder (engine created with stream_slots > 0) --------------------------------
+    @property
+    def stream_slots(self) -> int:
+        return int(self.cfg.stream_slots)
+
+    def ae_encode_stream(self, slot: int, audio):
+        """One buffer through the streaming export's ``encode`` (export_autoencoder.py AE_notcausal): (B,1,S) -> (B,Z,S/ratio)."""
+        audio = self._dev(audio, "audio")
+        B, _, S = audio.shape
+        r = self.ae_ratio
+        if r == 0 or S % r:
+            raise ValueError(f"samples ({S}) must be a multiple of the codec ratio ({r})")
+        z = torch.empty(B, self.cfg.ae_z_channels, S // r, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_ae_encode_stream(self._h, int(slot), audio.data_ptr(), z.data_ptr(), B, S, self._stream()),
+                    self._h, "after_ae_encode_stream")
+        return z
+
+    def ae_decode_stream(self, slot: int, z):
+        """One buffer through the streaming export's overlap-add ``decode`` (export_autoencoder.py:128-153)."""
+        z = self._dev(z, "z")
+        B, Cz, T = z.shape
+        if Cz != self.cfg.ae_z_channels:
+            raise ValueError(f"z must have {self.cfg.ae_z_channels} channels")
+        audio = torch.empty(B, 1, T * self.ae_ratio, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_ae_decode_stream(self._h, int(slot), z.data_ptr(), audio.data_ptr(), B, T, self._stream()),
+                    self._h, "after_ae_decode_stream")
+        return audio
+
+    def structure_encode_stream(self, slot: int, z):
+        """``Encoder1D.forward_stream`` (encoder.py:300-322) with cached convolutions."""
+        z = self._dev(z, "z")
+        B, Cin, T = z.shape
+        out = torch.empty(B, self.cfg.se_channels[self.cfg.se_n_blocks - 1], T, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_structure_encode_stream(self._h, int(slot), z.data_ptr(), out.data_ptr(), B, T, self._stream()),
+                    self._h, "after_structure_encode_stream")
+        return out
+
+    def stream_reset(self, slot: int):
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_stream_reset(self._h, int(slot), self._stream()), self._h, "after_stream_reset")
 
     def structure_encode(self, z):
         z = self._dev(z, "z")

@@ -2,11 +2,15 @@
 ``Engine``.  Same method names, channel counts, ratios and attribute setters, so host code written against the exported
 model (notebooks/audio_to_audio_demo.ipynb cell 9, ``nn~ <model> generate_timbre 8192``) runs against it.
 
-Semantics.  Codec and conditioning encoders are *block-offline*: every call processes its buffer with the offline
-kernels, i.e. what the reference computes with ``cc.use_cached_conv(False)``; the cross-buffer state the reference keeps in
-cached convolutions is not carried over.  The denoiser IS streamed when the engine was created with ``max_cache_size > 0``
-(``export.py:74-79`` binds it to LOCAL_ATTENTION_SIZE): one rolling KV history per diffusion step, exactly as in
-``export.py:398-416``.  The rolling ``previous_timbre`` latent buffer, part of the method contract, is kept.
+Semantics.  On an engine created with ``stream_slots >= 2`` and ``max_cache_size > 0`` every stage carries the state the
+exported model carries: the two codec copies (``emb_model_structure`` = slot 0, ``emb_model_timbre`` = slot 1,
+``export.py:161-168``) run the streaming export of the codec (cached-conv encoder, CachedGroupNorm stream branch,
+overlap-add decoder: ``export_autoencoder.py:16-153``), ``structure`` runs ``Encoder1D.forward_stream`` with cached convs,
+the denoiser keeps one rolling KV history per diffusion step (``export.py:398-416``), and the timbre encoder sees the rolling
+``previous_timbre`` latent buffer (``ECAPATDNN.forward_stream`` is stateless).  On an engine without streaming state the
+corresponding stage processes each buffer on its own with the offline kernels (what the reference computes with
+``cc.use_cached_conv(False)``).  A freshly created engine starts from zero state; the exported ``.ts`` starts from the state
+its export script left behind after its silent test passes -- ``prime_like_export()`` replays those.
 TorchScript serialisation (``export_to_ts``) and the latent-map MLP (``latent2map`` / ``map2latent``) are out of scope.
 """
 from __future__ import annotations
@@ -92,9 +96,34 @@ class Streamer:
         return self.engine.sample(x_last, cond, time_cond, self.nb_steps[0], self.guidance_timbre[0],
                                   self.guidance_structure[0], cfg_variant=L.CFG_AUDIO, clamp=0.1)
 
+    # codec copies of the exported model (export.py:161-168): slot 0 = emb_model_structure, slot 1 = emb_model_timbre
+    def _encode(self, slot: int, x):
+        if self.engine.stream_slots > slot:
+            return self.engine.ae_encode_stream(slot, x)
+        return self.engine.ae_encode(x)
+
+    def prime_like_export(self, n_batch: int = 1):
+        """A loaded ``export_stream.ts`` does not start from zero state: the export scripts ran silence through it.
+        Replayed here, per codec copy: the two 131072-sample (64-frame) silent ``encode`` passes of
+        export_autoencoder.py (:49-51 constructor, :314-315 main) and the ``decode`` of the second one (:316), then the
+        16384-sample ``encode`` of export.py:173-174 on the structure copy.  NOT replayed: the constructor's plain
+        ``model.decode`` of the throw-away offline encoder's latents (:51), which only seeds the decoder's GroupNorm
+        history -- that history is fully overwritten after 64 latent frames (12 s) of real audio."""
+        eng = self.engine
+        if eng.stream_slots < 2:
+            raise RuntimeError("prime_like_export needs an engine with stream_slots >= 2")
+        if (eng.cfg.stream_max_frames or 64) < 64:
+            raise RuntimeError("prime_like_export replays 64-frame buffers: create the engine with stream_max_frames >= 64")
+        silence = torch.zeros(n_batch, 1, 64 * self.ae_ratio, device=eng.device)
+        for slot in (0, 1):
+            eng.ae_encode_stream(slot, silence)
+            z = eng.ae_encode_stream(slot, silence)
+            eng.ae_decode_stream(slot, z)
+        eng.ae_encode_stream(0, silence[..., :8 * self.ae_ratio].contiguous())
+
     def timbre(self, x):
         x = self._check("timbre", x)
-        z = self.engine.ae_encode(x)
+        z = self._encode(1, x)
         n, t = z.shape[0], z.shape[-1]
         hist = torch.cat((self.previous_timbre[:n], z), -1)[..., t:]
         self.previous_timbre[:n] = hist
@@ -103,7 +132,10 @@ class Streamer:
 
     def structure(self, x):
         x = self._check("structure", x)
-        return self.engine.structure_encode(self.engine.ae_encode(x))
+        z = self._encode(0, x)
+        if self.engine.stream_slots > 0:
+            return self.engine.structure_encode_stream(0, z)  # encoder_time.forward_stream (export.py:431-435)
+        return self.engine.structure_encode(z)
 
     def diffuse(self, x, noise: Optional[torch.Tensor] = None):
         """(n, zs + zt, T) -> (n, latents, T).  As in the reference only batch row 0 is sampled and the result is
@@ -131,7 +163,10 @@ class Streamer:
         return out.repeat(n, 1, 1) if n > 1 else out
 
     def decode(self, x):
-        return self.engine.ae_decode(self._check("decode", x))
+        x = self._check("decode", x)
+        if self.engine.stream_slots > 0:
+            return self.engine.ae_decode_stream(0, x)  # emb_model_structure.decode (export.py:451-455)
+        return self.engine.ae_decode(x)
 
     def generate(self, x, noise: Optional[torch.Tensor] = None):
         return self.decode(self.diffuse(x, noise))

@@ -135,6 +135,13 @@ typedef struct after_config {
   int32_t un_cond_channels;               /* 0: no global condition */
   int32_t un_n_attn_layers;
   int32_t un_use_res_last;
+  /* --- streaming codec / structure encoder: what the exported models compute buffer by buffer
+   *     (after_scripts/export_autoencoder.py:16-153, 305-319; after_scripts/export.py:14-17, 418-435).  stream_slots
+   *     independent states (the exported Streamer holds two codec copies: structure and timbre); 0 = offline only. --- */
+  int32_t stream_slots;
+  int32_t stream_max_frames; /* latent frames per streaming call the state is sized for (0: 64) */
+  int32_t stream_gn_frames;  /* CachedGroupNorm padding_size in latent frames = length of the export script's first call
+                                (131072 samples = 64 frames, export_autoencoder.py:49-51; 0: 64) */
 } after_config;
 
 typedef struct after_ctx* after_handle;
@@ -220,6 +227,24 @@ int after_ae_encode(after_handle h, const float* audio, float* z, int B, int64_t
 
 /* AutoEncoder.decode (SimpleNetsStream.py:943-954): z dev (B,Z,T) -> audio dev (B,1,T*ratio). */
 int after_ae_decode(after_handle h, const float* z, float* audio, int B, int T, void* stream);
+
+/* ---- streaming codec and structure encoder (needs after_config.stream_slots > 0) ----
+ * What `export_stream.ts` of a non-causal AutoEncoder computes per buffer (export_autoencoder.py AE_notcausal):
+ * after_ae_encode_stream: offline PQMF of the buffer, then the encoder with cached convolutions (every conv keeps the last
+ *   l + r + stride-delay frames of its input; residual branches delayed to match) and CachedGroupNorm(stream=True)
+ *   (statistics over the previous stream_gn_frames + this buffer); the latents lag the offline encoder by its cumulative
+ *   delay (8 frames for baseAE).  audio dev (B,1,S) -> z dev (B,Z,S/ratio).
+ * after_ae_decode_stream: offline decoder over [z_buffer ; z] with CachedGroupNorm(stream=True), linear cross-fade of the
+ *   first 4 latent frames with the tail kept from the previous call (export_autoencoder.py:128-153).  z dev (B,Z,T>=4) ->
+ *   audio dev (B,1,T*ratio).
+ * after_structure_encode_stream: Encoder1D.forward_stream (encoder.py:300-322) with cached convolutions.
+ * after_stream_reset: state of a freshly constructed model (zero caches) for one slot.
+ * cached_conv (acids-ircam/cached_conv >= 2.5.0) is an un-vendored dependency of the reference; its semantics are restated
+ * in oracle/after_oracle_stream.py. */
+int after_ae_encode_stream(after_handle h, int slot, const float* audio, float* z, int B, int64_t samples, void* stream);
+int after_ae_decode_stream(after_handle h, int slot, const float* z, float* audio, int B, int T, void* stream);
+int after_structure_encode_stream(after_handle h, int slot, const float* z, float* time_cond, int B, int T, void* stream);
+int after_stream_reset(after_handle h, int slot, void* stream);
 
 /* Encoder1D.forward (encoder.py:273-298): z dev (B,C,T) -> time_cond dev (B,zs,T). */
 int after_structure_encode(after_handle h, const float* z, float* time_cond, int B, int T, void* stream);

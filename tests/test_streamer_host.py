@@ -21,6 +21,7 @@ class OracleEngine:
         self.cfg = types.SimpleNamespace(tcond_dim=den_cfg.tcond_dim, cond_dim=den_cfg.cond_dim, n_channels=den_cfg.n_channels,
                                          drop_value=drop_value, max_cache_size=den_cfg.local_attention_size if streaming else 0)
         self.ae_ratio = acfg.ratio
+        self.stream_slots = 0  # offline codec / encoders (the streaming ones are covered by the -m gpu tests)
         self.has_denoiser = self.has_codec = self.has_timbre = True
         self.has_structure = se_cfg is not None
         self.sd_den = synth.denoiser_state_dict(den_cfg, 1)
