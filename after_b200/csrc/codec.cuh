@@ -477,13 +477,26 @@ struct ConvNet {
     OperandOut o;
     if (tc_mode() && consumer.w.tc_ok) { o.hi = dst->hi; o.lo = nprod() > 1 ? dst->lo : nullptr; }
     else o.f32 = dst->f32;
-    const int fpb = std::max(1, 8192 / Cp);
-    dim3 grid(ceil_div(T, fpb), B);
-    const size_t smem = (size_t)5 * C * sizeof(float);
     const double el = (double)B * T;
     ProfScope prof(KC_ACT_OPERAND, st, 0.0, el * (4.0 * C + Cp * (o.f32 ? 4.0 : (o.lo ? 4.0 : 2.0))));
-    if (C % 4 == 0 && Cp % 4 == 0) launch_k(act_operand_kernel<4>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
-    else launch_k(act_operand_kernel<1>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
+    const int q = Cp / 4;
+    int R = 0;  // frame rows per block of the register-parameter kernel: q * R threads, a multiple of 32, <= 256
+    if (C % 4 == 0 && Cp % 4 == 0 && q <= 256)
+      for (int r = 256 / q; r >= 1; --r)
+        if ((q * r) % 32 == 0) { R = r; break; }
+    if (R > 0) {
+      // ~32 K elements per block, but at least ~4 blocks per SM over the whole launch
+      int fpb = std::max(R, 32768 / Cp);
+      while (fpb > 4 * R && (long long)ceil_div(T, fpb) * B < 592) fpb /= 2;
+      fpb = ceil_div(fpb, R) * R;
+      launch_k(act_operand_rows_kernel, dim3(ceil_div(T, fpb), B), dim3(q * R), 0, st, x, o, p, T, C, Cp, fpb, out_T, out_t0, R);
+    } else {
+      const int fpb = std::max(1, 8192 / Cp);
+      dim3 grid(ceil_div(T, fpb), B);
+      const size_t smem = (size_t)5 * C * sizeof(float);
+      if (C % 4 == 0 && Cp % 4 == 0) launch_k(act_operand_kernel<4>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
+      else launch_k(act_operand_kernel<1>, grid, dim3(256), smem, st, x, o, p, T, C, Cp, fpb, out_T, out_t0);
+    }
     AFTER_COUNT_LAUNCH();
   }
 

@@ -143,6 +143,79 @@ act_operand_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int
   }
 }
 
+// Fast path of the operand pass (C % 4 == 0): the block is (Cp / 4) channel quads x R frame rows, so a thread's
+// channel quad never changes: its folded norm (y = x * sc + sh) and Snake parameters live in registers, the frame loop is
+// load float4 -> 2 FMA + Snake -> bf16 split -> store, with no shared memory and no index division.  (ncu on the generic
+// kernel above, baseAE encode at 8 chunks: 49 instructions per element at 71 % issue utilisation -- the index
+// division and 20 shared-memory parameter loads per 4 elements were half of them; profiles/r02a_ncu_codec_full.json.)
+// grid = (ceil(T / frames_per_block), B), block = (Cp / 4) * R threads (a multiple of 32, <= 256).
+__global__ void __launch_bounds__(256)
+act_operand_rows_kernel(const float* __restrict__ x, OperandOut out, ActParams p, int T, int C, int Cp, int frames_per_block,
+                        int out_T, int out_t0, int R) {
+  pdl_wait();
+  pdl_trigger();
+  const int q = Cp >> 2;               // channel quads per frame
+  const int cq = threadIdx.x % q;      // one division per thread, outside the loop
+  const int row = threadIdx.x / q;
+  const int c = cq * 4;
+  const int b = blockIdx.y;
+  const bool live = c < C;             // quads in [C, Cp) are zero padding
+  // y = (x - mu) * rs + be, in exactly that form (the generic kernel and the oracle round the same way)
+  float mu4[4] = {0.f, 0.f, 0.f, 0.f}, rs4[4] = {1.f, 1.f, 1.f, 1.f}, be4[4] = {0.f, 0.f, 0.f, 0.f};
+  float al[4] = {0.f, 0.f, 0.f, 0.f}, ib[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p.norm == NORM_GROUP) {
+        const int cpg = C / p.groups;
+        const int g = (c + j) / cpg;
+        const double n = (double)cpg * (double)(p.stat_frames > 0 ? p.stat_frames : T);
+        const double s = p.stats[((size_t)b * p.groups + g) * 2];
+        const double qq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+        const double mean = s / n;
+        double var = qq / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mu4[j] = (float)mean;
+        rs4[j] = (float)(1.0 / sqrt(var + 1e-5)) * p.gamma[c + j];
+        be4[j] = p.beta[c + j];
+      } else if (p.norm == NORM_AFFINE) {
+        mu4[j] = p.mu[c + j]; rs4[j] = p.rs[c + j]; be4[j] = p.be[c + j];
+      }
+      if (p.act == ACT_SNAKE) { al[j] = p.alpha[c + j]; ib[j] = p.inv_beta[c + j]; }
+    }
+  }
+  const int t0 = blockIdx.x * frames_per_block;
+  const int nt = min(frames_per_block, T - t0);
+  const float* xin = x + ((size_t)b * T + t0) * C + c;
+  const size_t obase = ((size_t)b * out_T + out_t0 + t0) * Cp + c;
+#pragma unroll 4
+  for (int f = row; f < nt; f += R) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float4 xv = *reinterpret_cast<const float4*>(xin + (size_t)f * C);
+      v[0] = xv.x; v[1] = xv.y; v[2] = xv.z; v[3] = xv.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = (v[j] - mu4[j]) * rs4[j] + be4[j];
+        if (p.act == ACT_SNAKE) y = snake_beta(y, al[j], ib[j]);
+        else if (p.act == ACT_SILU) y = silu(y);
+        v[j] = y;
+      }
+    }
+    const size_t off = obase + (size_t)f * Cp;
+    if (out.f32) *reinterpret_cast<float4*>(out.f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+    if (out.hi) {
+      __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out.hi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+      if (out.lo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+        *reinterpret_cast<uint2*>(out.lo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+      }
+    }
+  }
+}
+
 // Stand-alone GroupNorm statistics of x (B, T, C): stats[b][g] += {sum, sum of squares}.  Used where the producer
 // is not a tap-GEMM epilogue (PQMF output, naive-kernel layers).  grid = (ceil(T / 256), B), 256 threads.
 __global__ void __launch_bounds__(256)
