@@ -17,6 +17,7 @@
 #include "context.cuh"
 #include "denoiser_kernels.cuh"
 #include "gemm_host.cuh"
+#include "stream_step.cuh"
 
 namespace after {
 
@@ -62,6 +63,8 @@ struct Denoiser {
   static constexpr int SKINNY_ROWS = 16;
   float *sk_a = nullptr, *sk_hid = nullptr;     // [SKINNY_ROWS][D], [SKINNY_ROWS][HID]
   bool skinny_now = false;
+  unsigned* stream_barrier = nullptr;           // grid-barrier counter of the persistent streaming-block kernel
+  int n_sms = 0;
 
   // graph cache
   struct GraphEntry {
@@ -209,6 +212,15 @@ struct Denoiser {
       sk_hid = arena->alloc<float>((size_t)SKINNY_ROWS * HID);
       AFTER_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<SKINNY_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float))));
+      stream_barrier = arena->alloc<unsigned>(4);
+      const int ss_bytes = (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float));
+      AFTER_REQUIRE(ss_bytes <= 200 * 1024, AFTER_EINVAL, "embed_dim * mlp_multiplier too large for the streaming kernels");
+      auto set_ss = [&](const void* f) { AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ss_bytes)); };
+      set_ss((const void*)stream_block_kernel<8, 12>); set_ss((const void*)stream_block_kernel<8, 20>); set_ss((const void*)stream_block_kernel<8, 32>);
+      set_ss((const void*)stream_block_kernel<4, 12>); set_ss((const void*)stream_block_kernel<4, 20>); set_ss((const void*)stream_block_kernel<4, 32>);
+      int dev = 0;
+      AFTER_CUDA_CHECK(cudaGetDevice(&dev));
+      AFTER_CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const char* ng = debug_env("AFTER_NO_GRAPH");
     use_graph = !(ng && ng[0] == '1');
@@ -582,8 +594,44 @@ struct Denoiser {
 
   // stream = true is one audio block of the exported Streamer.sample (after_scripts/export.py:398-416): Euler step s runs
   // against KV cache s, which is then rolled by the block length.
+  // A live streaming block (rows = 3 B T <= 16) runs as ONE persistent kernel: all Euler steps, all layers, CFG combine and
+  // roll_cache, separated by grid barriers instead of 28 launches per step (stream_step.cuh).
+  bool persistent_stream_ok(int B, int T) const {
+    static int off = -1;
+    if (off < 0) { const char* e = debug_env("AFTER_STREAM_PERSISTENT"); off = (e && e[0] == '0') ? 1 : 0; }
+    return !off && !g_prof.on && cacheW > 0 && sk_a != nullptr && 3 * B * T <= SKINNY_ROWS && L <= 8 && n_sms > 0 && D % 128 == 0;
+  }
+  void stream_block_persistent(int B, int T, int nb_steps, cudaStream_t st) {
+    StreamNetDev net{};
+    for (int l = 0; l < L; ++l) {
+      const DenoiserLayer& ly = layers[l];
+      net.layer[l] = StreamLayerDev{ly.qkv.w, ly.mlp0.w, ly.mlp0.bias, ly.mlp2.w, ly.mlp2.bias, ly.n1_g, ly.n1_b, ly.n3_g, ly.n3_b};
+    }
+    net.L = L; net.D = D; net.HID = HID; net.C = C; net.chunk = cfg.attention_chunk_size; net.window = cfg.local_attention_size;
+    net.W = cacheW; net.maxN = maxN; net.maxRows = maxRows; net.ada_ld = L * 2 * D;
+    net.pe_wt = pe_wt; net.pe_b = pe_b; net.out_w = out_proj.w; net.out_b = out_proj.bias;
+    net.rope_tab = rope_tab; net.adaT = adaT; net.adaC = adaC; net.map = seqmap(); net.guidance = guidance;
+    net.x_state = x_state; net.h0 = h0; net.hA = h_part; net.hB = h; net.qkv_stream = qkv_stream; net.sk_a = sk_a; net.sk_hid = sk_hid;
+    net.proj = proj; net.kcache = kcache; net.vcache = vcache;
+    net.cache_slab = cache_slab(); net.adaC_step_stride = (size_t)(B + 1) * L * 2 * D; net.barrier = stream_barrier;
+    AFTER_CUDA_CHECK(cudaMemsetAsync(stream_barrier, 0, sizeof(unsigned), st));
+    const size_t smem = (size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float);
+    const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
+    PdlScope pdl(false);  // plain launch: every CTA must become resident for the grid barrier, nothing to overlap with
+#define AFTER_LAUNCH_SS(NH, MK) launch_k(stream_block_kernel<NH, MK>, dim3(n_sms), dim3(256), smem, st, net, B, T, nb_steps)
+    if (H == 8) { if (mk <= 12) AFTER_LAUNCH_SS(8, 12); else if (mk <= 20) AFTER_LAUNCH_SS(8, 20); else AFTER_LAUNCH_SS(8, 32); }
+    else        { if (mk <= 12) AFTER_LAUNCH_SS(4, 12); else if (mk <= 20) AFTER_LAUNCH_SS(4, 20); else AFTER_LAUNCH_SS(4, 32); }
+#undef AFTER_LAUNCH_SS
+    AFTER_COUNT_LAUNCH();
+    last_N = 3 * B; last_T = T;
+  }
+
   void sample_body(int B, int T, int nb_steps, cudaStream_t st, bool stream = false) {
     build_tables(B, T, nb_steps * (B + 1), 0, B, B + 1, st);
+    if (stream && persistent_stream_ok(B, T)) {
+      stream_block_persistent(B, T, nb_steps, st);
+      return;
+    }
     const size_t step_stride = (size_t)(B + 1) * L * 2 * D;
     for (int s = 0; s < nb_steps; ++s) {
       run_network(x_state, B, 3 * B, T, adaC + (size_t)s * step_stride, st, stream ? s : -1);
