@@ -216,8 +216,8 @@ struct Denoiser {
       const int ss_bytes = (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float));
       AFTER_REQUIRE(ss_bytes <= 200 * 1024, AFTER_EINVAL, "embed_dim * mlp_multiplier too large for the streaming kernels");
       auto set_ss = [&](const void* f) { AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ss_bytes)); };
-      set_ss((const void*)stream_block_kernel<8, 12>); set_ss((const void*)stream_block_kernel<8, 20>); set_ss((const void*)stream_block_kernel<8, 32>);
-      set_ss((const void*)stream_block_kernel<4, 12>); set_ss((const void*)stream_block_kernel<4, 20>); set_ss((const void*)stream_block_kernel<4, 32>);
+      set_ss((const void*)stream_block_kernel<8, 12, 512>); set_ss((const void*)stream_block_kernel<8, 20, 256>); set_ss((const void*)stream_block_kernel<8, 32, 256>);
+      set_ss((const void*)stream_block_kernel<4, 12, 512>); set_ss((const void*)stream_block_kernel<4, 20, 256>); set_ss((const void*)stream_block_kernel<4, 32, 256>);
       int dev = 0;
       AFTER_CUDA_CHECK(cudaGetDevice(&dev));
       AFTER_CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -618,9 +618,9 @@ struct Denoiser {
     const size_t smem = (size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float);
     const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
     PdlScope pdl(false);  // plain launch: every CTA must become resident for the grid barrier, nothing to overlap with
-#define AFTER_LAUNCH_SS(NH, MK) launch_k(stream_block_kernel<NH, MK>, dim3(n_sms), dim3(256), smem, st, net, B, T, nb_steps)
-    if (H == 8) { if (mk <= 12) AFTER_LAUNCH_SS(8, 12); else if (mk <= 20) AFTER_LAUNCH_SS(8, 20); else AFTER_LAUNCH_SS(8, 32); }
-    else        { if (mk <= 12) AFTER_LAUNCH_SS(4, 12); else if (mk <= 20) AFTER_LAUNCH_SS(4, 20); else AFTER_LAUNCH_SS(4, 32); }
+#define AFTER_LAUNCH_SS(NH, MK, NT) launch_k(stream_block_kernel<NH, MK, NT>, dim3(n_sms), dim3(NT), smem, st, net, B, T, nb_steps)
+    if (H == 8) { if (mk <= 12) AFTER_LAUNCH_SS(8, 12, 512); else if (mk <= 20) AFTER_LAUNCH_SS(8, 20, 256); else AFTER_LAUNCH_SS(8, 32, 256); }
+    else        { if (mk <= 12) AFTER_LAUNCH_SS(4, 12, 512); else if (mk <= 20) AFTER_LAUNCH_SS(4, 20, 256); else AFTER_LAUNCH_SS(4, 32, 256); }
 #undef AFTER_LAUNCH_SS
     AFTER_COUNT_LAUNCH();
     last_N = 3 * B; last_T = T;

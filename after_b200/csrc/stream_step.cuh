@@ -5,7 +5,10 @@
 // Why: a 12-row step is 28 kernels of a few microseconds of work each; as separate launches (even inside a CUDA graph
 // with programmatic dependent launch) a step costs ~266 us, i.e. ~9.5 us per kernel of launch / drain latency
 // (profiles/r01c_launches_stream_summary.txt).  Here one CTA per SM stays resident and the 27 phases of a step are
-// separated by a grid barrier (~1.5 us: one atomic per CTA + a polled acquire load) instead of a kernel boundary.
+// separated by a grid barrier (one atomic per CTA + a polled acquire load) instead of a kernel boundary.
+// Measured (base, B = 1, 4 frames, 8 steps): 2.15 ms as 28 launches per step -> 1.76 ms (221 us per step; the tiny model,
+// with a quarter of the weights, 156 us): what is left is ~6 us per phase of barrier + three dependent L2 round trips.
+// Tried and dropped: requesting a phase's first weights before the barrier (register spills at 512 threads, no gain).
 //
 // Phases of a step (B = barrier):
 //   embed        h0[(b,t)] = GELU(W_in x + b_in)                                          (transformerv2.py:387-391)   B
@@ -73,13 +76,23 @@ __device__ __forceinline__ void ss_linear(const float* As, const float* __restri
 #pragma unroll
     for (int m = 0; m < SS_MAXM; ++m) acc[m] = 0.f;
     const float* wr = Wm + (size_t)n * K;
-    for (int k = lane * 4; k < K; k += 128) {
-      const float4 w = *reinterpret_cast<const float4*>(wr + k);
+    // four 512-byte weight loads in flight per warp: with one load per iteration a warp waited a whole L2 round trip per
+    // 128 weights and the 57 MB of weights of a step streamed at 0.44 TB/s chip-wide (measured: 266 -> 221 us per step)
+    for (int k0 = lane * 4; k0 < K; k0 += 512) {
+      float4 w[4];
 #pragma unroll
-      for (int m = 0; m < SS_MAXM; ++m) {
-        if (m < M) {
-          const float4 a = *reinterpret_cast<const float4*>(As + m * K + k);
-          acc[m] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[m]))));
+      for (int u = 0; u < 4; ++u)
+        w[u] = k0 + 128 * u < K ? *reinterpret_cast<const float4*>(wr + k0 + 128 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + 128 * u < K) {
+#pragma unroll
+          for (int m = 0; m < SS_MAXM; ++m) {
+            if (m < M) {
+              const float4 a = *reinterpret_cast<const float4*>(As + m * K + k0 + 128 * u);
+              acc[m] = fmaf(a.x, w[u].x, fmaf(a.y, w[u].y, fmaf(a.z, w[u].z, fmaf(a.w, w[u].w, acc[m]))));
+            }
+          }
         }
       }
     }
@@ -105,11 +118,14 @@ __device__ __forceinline__ void ss_load_rows(float* As, const float* __restrict_
   __syncthreads();
 }
 
-template <int NH, int MAXK>
-__global__ void __launch_bounds__(256, 1)
+// NT threads per CTA: 512 where the attention phase's registers allow it (MAXK <= 12), so that the 3 D / 3 x D output columns
+// of the big projections are at most one per warp on 148 SMs; else 256.
+template <int NH, int MAXK, int NT>
+__global__ void __launch_bounds__(NT, 1)
 stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int nb_steps) {
   constexpr int D = NH * 64;
   constexpr int NV = D / 32;
+  constexpr int NWARPS = NT / 32;
   extern __shared__ __align__(16) float ss_smem[];  // [M][max(D, HID)] operand rows; the attention phase uses its head
   pdl_wait();
   pdl_trigger();
@@ -123,14 +139,23 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
     const float* adaC = net.adaC + (size_t)s * net.adaC_step_stride;
     float* kc_s = net.kcache + (size_t)s * net.cache_slab;
     float* vc_s = net.vcache + (size_t)s * net.cache_slab;
-    // ---- embed: B T rows x D outputs, one output per thread
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * T * D; i += nb * blockDim.x) {
-      const int d = i % D, r = i / D;
-      const int b = r / T, t = r - b * T;
-      float acc = net.pe_b[d];
-      const float* xp = net.x_state + (size_t)b * net.C * T + t;
-      for (int c = 0; c < net.C; ++c) acc = fmaf(xp[(size_t)c * T], net.pe_wt[(size_t)c * D + d], acc);
-      net.h0[(size_t)r * D + d] = gelu_erf(acc);
+    // ---- embed: B T rows x D outputs, one output per thread; the B T x C inputs staged in shared memory
+    {
+      const int nx = B * T * net.C;
+      for (int i = threadIdx.x; i < nx; i += blockDim.x) {  // ss_smem[(b, t), c]
+        const int c = i % net.C, r = i / net.C;
+        const int b = r / T, t = r - b * T;
+        ss_smem[i] = net.x_state[((size_t)b * net.C + c) * T + t];
+      }
+      __syncthreads();
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * T * D; i += nb * blockDim.x) {
+        const int d = i % D, r = i / D;
+        float acc = net.pe_b[d];
+        const float* xs = ss_smem + (size_t)r * net.C;
+#pragma unroll 16
+        for (int c = 0; c < net.C; ++c) acc = fmaf(xs[c], net.pe_wt[(size_t)c * D + d], acc);
+        net.h0[(size_t)r * D + d] = gelu_erf(acc);
+      }
     }
     ss_grid_sync(net.barrier, target, nb);
 
@@ -138,7 +163,7 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
       const StreamLayerDev& ly = net.layer[l];
       float* qkv_l = net.qkv_stream + (size_t)l * net.maxRows * 3 * D;
       // ---- phase A: LN0 -> AdaLN-t -> (publish h) -> LN1 -> operand rows in shared memory, then the QKV projection
-      for (int row = warp; row < M; row += 8) {
+      for (int row = warp; row < M; row += NWARPS) {
         const int n = row / T, t = row - n * T;
         const float* hp = l == 0 ? net.h0 + (size_t)(net.map.src_seq[n] * T + t) * D : net.hA + (size_t)row * D;
         const float* ap = net.adaT + (size_t)(net.map.t_row0[n] + t * net.map.t_stride[n]) * net.ada_ld + l * 2 * D;
@@ -318,9 +343,18 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
         const int l = i / (2 * D * N3);
         float* c = (which ? vc_s : kc_s) + ((size_t)l * net.maxN + n) * W * D;
         const float* last = net.qkv_stream + ((size_t)l * net.maxRows + (size_t)n * T) * (3 * D) + (which ? 2 * D : D);
-        for (int j = 0; j < W; ++j) {
-          const int src = j + r;
-          c[(size_t)j * D + d] = src < W ? c[(size_t)src * D + d] : last[(size_t)(src - W) * (3 * D) + d];
+        // ascending chunks of 8 slots: a chunk's sources (index >= its first slot + r) are all read before any of its
+        // slots is written, and earlier chunks only wrote lower slots -- in place, with 8 independent loads in flight
+        for (int j0 = 0; j0 < W; j0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int src = j0 + u + r;
+            if (j0 + u < W) v[u] = src < W ? c[(size_t)src * D + d] : last[(size_t)(src - W) * (3 * D) + d];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (j0 + u < W) c[(size_t)(j0 + u) * D + d] = v[u];
         }
       }
     }
