@@ -371,8 +371,38 @@ def main():
                   "median_ms_per_block": per_blk[len(per_blk) // 2], "p95_ms_per_block": per_blk[int(len(per_blk) * 0.95)],
                   "diffusion_steps_per_s": s_steps / (per_blk[len(per_blk) // 2] / 1e3),
                   "realtime_margin": blk_audio_ms / per_blk[len(per_blk) // 2],
-                  "what": "after_sample_stream: one CUDA-graph replay per block (sampler only; codec not included)"}
+                  "what": "after_sample_stream: one persistent kernel per block (all Euler steps, layers, CFG, roll_cache; "
+                          "sampler only)"}
         s_eng.close()
+        # the whole exported Streamer.forward on one 8192-sample buffer (export.py:398-455): two streaming codec encodes,
+        # Encoder1D.forward_stream, ECAPA on the rolling timbre buffer, the streamed sampler, overlap-add decode
+        if chain and se_sd is not None:
+            from after_b200.streamer import Streamer
+            f_eng = Engine(model=mc, autoencoder=acfg, denoiser_state=den_sd, autoencoder_state=ae_sd, structure_state=se_sd,
+                           timbre_state=te_sd, precision=args.precision, device=local, max_batch=1, max_steps=s_steps, seq_len=64,
+                           max_samples=64 * 2048, max_cache_size=mc.denoiser.local_attention_size, stream_slots=2,
+                           stream_max_frames=s_frames)
+            stm = Streamer(f_eng, n_signal_timbre=64, chunk_size=4)
+            stm.set_nb_steps(s_steps); stm.set_guidance_timbre(2.0); stm.set_guidance_structure(1.0)
+            buf = torch.cat([synth.synth_audio(1, s_frames * 2048, seed=3), synth.synth_audio(1, s_frames * 2048, seed=4)], 1).to(dev)
+            noise = torch.randn(1, 64, s_frames, device=dev)
+            for _ in range(5):
+                stm.forward(buf, noise=noise)
+            torch.cuda.synchronize()
+            wall = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                stm.forward(buf, noise=noise)
+                torch.cuda.synchronize()
+                wall.append((time.perf_counter() - t0) * 1e3)
+            wall.sort()
+            stream["streamer_forward"] = {
+                "median_ms_per_buffer": wall[len(wall) // 2], "p95_ms_per_buffer": wall[int(len(wall) * 0.95)],
+                "realtime_margin": blk_audio_ms / wall[len(wall) // 2],
+                "what": "Streamer.forward on one 8192-sample buffer, host wall clock incl. launches and the final sync: 2 x "
+                        "after_ae_encode_stream + after_structure_encode_stream + after_timbre_encode + after_sample_stream + "
+                        "after_ae_decode_stream (device-resident buffers)"}
+            f_eng.close()
 
     # ---- roofline of the dominant kernel (tcgen05 tap-GEMM), per-launch CUDA events on the launching stream ----------
     pk = peaks()
