@@ -485,6 +485,50 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
   __syncwarp();
 }
 
+// Up-projection epilogue with TMA stores: lane l holds row l of a 32 x 16 half-block (the TMEM 32x32b layout); bias and
+// GELU are applied in place, the bf16 hi (and lo) rows -- 32 bytes each -- go row-major into the warp's 2 KB staging tile
+// and ONE lane issues a 3-D cp.async.bulk.tensor store per array (frames beyond T are clipped by the TMA unit).  Against
+// epi_block this drops the shared-memory transposition (4 st + 4 ld.shared.v4), the per-row address arithmetic and 8
+// global store instructions per lane; the staging tile is reused as soon as the previous store has READ it
+// (cp.async.bulk.wait_group.read), which the next half-block's TMEM load and GELU cover.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void epi_block_gelu_tma(const CUtensorMap* o_hi, const CUtensorMap* o_lo, bool want_lo, float* stg,
+                                                   const uint32_t* v, const float* __restrict__ bias, int b, int t_base,
+                                                   int col0, int lane) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + col0 + 4 * i);  // same address in every lane: one broadcast
+    const float2 g0 = gelu_erf_fast2(make_float2(__uint_as_float(v[4 * i]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y));
+    const float2 g1 = gelu_erf_fast2(make_float2(__uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w));
+    uint2 h2, l2;
+    split4_bf16(make_float4(g0.x, g0.y, g1.x, g1.y), h2, l2);
+    hi[2 * i] = h2.x; hi[2 * i + 1] = h2.y;
+    lo[2 * i] = l2.x; lo[2 * i + 1] = l2.y;
+  }
+  // the previous half-block's stores must have read the staging tile before it is overwritten
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  uint4* sh = reinterpret_cast<uint4*>(stg) + lane * 2;         // hi tile: [32 rows][32 B]
+  uint4* sl = reinterpret_cast<uint4*>(stg) + 64 + lane * 2;    // lo tile behind it
+  sh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  sh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (want_lo) {
+    sl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    sl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(o_hi, stg, col0, t_base, b);
+    if (want_lo) tma_store_3d(o_lo, reinterpret_cast<const uint4*>(stg) + 64, col0, t_base, b);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -923,6 +967,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 // =====================================================================================
 struct LinearProblem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap o_hi, o_lo;  // TMA-store views (N, T, B) of the bf16 hi / lo outputs (up projection)
   GemmEpi epi;
   int Cin;        // K
   int n_tiles_n;  // N / BN
@@ -1148,9 +1193,7 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
           if (tr && c == cbeg) mark(9 + 4 * ti);
           const bool full = T - t_base >= 32;
           if (prob == 0) {  // hidden activations: bf16 hi (+ lo in the 3-product mode), never fp32 (launch_mlp_fused)
-            if (full && nprod > 1) epi_block<EPI_GELU, 6, true>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
-            else if (full) epi_block<EPI_GELU, 2, true>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
-            else epi_block<EPI_GELU>(p0.epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
+            epi_block_gelu_tma(&p0.o_hi, &p0.o_lo, nprod > 1, stg, v, p0.epi.bias, b, t_base, n0 + c, lane);
           } else if (full) {
             epi_block<EPI_PLAIN, -1, true>(pe1, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
           } else {
@@ -1164,9 +1207,14 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
       __syncwarp();
       if (lane == 0) {
         // hand the stored tile to the publisher BEFORE releasing the accumulator buffer: a warp can then reach its next
-        // arrival on the same pub_bar parity (tile ti + 2, same TMEM buffer) only after every warp has arrived for ti
-        if (prob == 0)
+        // arrival on the same pub_bar parity (tile ti + 2, same TMEM buffer) only after every warp has arrived for ti.
+        // "Stored" = this warp's TMA stores have COMPLETED (wait_group without .read), ordered before the release by a
+        // proxy fence (the consumer reads them back through the async proxy after its acquire).
+        if (prob == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
           asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&pub_bar[ti & 1])) : "memory");
+        }
         mbar_arrive_cluster(buf ? te1 : te0);
       }
       if (warp == 2 && lane == 0) mark(prob ? 6 : 5);

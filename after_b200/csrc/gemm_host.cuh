@@ -57,6 +57,21 @@ inline CUtensorMap make_tmap_act(const void* ptr, int C, int P, int T, int B, si
   return m;
 }
 
+// Output of a GEMM epilogue as a TMA *store* target: 3-D bf16 (N, T, B) with N fastest, box (16 columns, 32 frames, 1), no
+// swizzle: one epilogue warp's half-block.  Frames beyond T are clipped by the TMA unit (ragged last row block).
+inline CUtensorMap make_tmap_store16(const void* ptr, int N, int T, int B) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * T * 2};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AFTER_REQUIRE(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled(store) failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
 inline int pick_bn(int N, int n_per_phase = 0) {
   for (int bn : {128, 64, 32})
     if (N % bn == 0 && (n_per_phase == 0 || n_per_phase % bn == 0)) return bn;
@@ -101,6 +116,19 @@ struct ActOperand {
   struct Maps { CUtensorMap hi, lo; };
   std::map<std::tuple<int, int, int, int>, Maps> cache;
   size_t bstride = 0;  // elements between streams (0: densely packed); set once for a streaming conv's persistent operand
+  std::map<std::tuple<int, int, int>, Maps> store_cache;  // TMA-store views (N, T, B) of the same buffers
+  const Maps& store_maps(int N, int T, int B) {
+    auto key = std::make_tuple(N, T, B);
+    auto it = store_cache.find(key);
+    if (it == store_cache.end()) {
+      AFTER_REQUIRE((size_t)N * T * B <= capacity, AFTER_EINVAL, "activation view exceeds the operand buffer");
+      Maps m;
+      m.hi = make_tmap_store16(hi, N, T, B);
+      m.lo = make_tmap_store16(lo ? lo : hi, N, T, B);
+      it = store_cache.emplace(key, m).first;
+    }
+    return it->second;
+  }
   const Maps& maps(int C, int P, int T, int B) {
     auto key = std::make_tuple(C, P, T, B);
     auto it = cache.find(key);
@@ -284,6 +312,11 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
   p1.a_hi = m1.hi; p1.a_lo = m1.lo; p1.b_hi = W2.map2_hi; p1.b_lo = W2.map2_lo; p1.epi = epi1; p1.Cin = W2.Cin;
   p1.n_tiles_n = W2.N / BN; p1.n_tiles = p1.n_tiles_n * n_m_tiles;
   p0.ksplit = 1; p1.ksplit = 1;
+  {  // the up projection's epilogue stores its bf16 hi / lo tiles with TMA (epi_block_gelu_tma)
+    const ActOperand::Maps& sm = hid.store_maps(W0.N, T, B);
+    p0.o_hi = sm.hi; p0.o_lo = sm.lo;
+    p1.o_hi = sm.hi; p1.o_lo = sm.lo;  // unused
+  }
   // only when the down projection has too few tiles to fill the machine (48 tiles on 74 CTA pairs at base B=8): with
   // many waves of tiles the split buys no balance and costs one extra write + read of the partial tensor
   if (partial && mlp_ksplit() == 2 && !epi1.out_hi && epi1.out_f32 && (W2.Cin / tc::BK) % 2 == 0 && p1.n_tiles < 2 * n_pairs) {
