@@ -242,8 +242,9 @@ class MidiStreamer:
                   cfg_variant=L.CFG_MIDI, clamp=0.1)
 
     def timbre(self, x):
+        """export_midi.py:383-398; the single codec copy ``emb_model_timbre`` (slot 0) streams when the engine has the state."""
         x = self._check("timbre", x)
-        z = self.engine.ae_encode(x)
+        z = self.engine.ae_encode_stream(0, x) if self.engine.stream_slots > 0 else self.engine.ae_encode(x)
         n, t = z.shape[0], z.shape[-1]
         self.previous_timbre[:n] = torch.cat((self.previous_timbre[:n], z), -1)[..., t:]
         zsem = self.engine.timbre_encode(self.previous_timbre[:n].contiguous())
@@ -277,7 +278,10 @@ class MidiStreamer:
         return out.repeat(n, 1, 1) if n > 1 else out
 
     def decode(self, x):
-        return self.engine.ae_decode(self._check("decode", x))
+        x = self._check("decode", x)
+        if self.engine.stream_slots > 0:
+            return self.engine.ae_decode_stream(0, x)  # emb_model_timbre.decode (export_midi.py:426-429)
+        return self.engine.ae_decode(x)
 
     def generate(self, x, noise: Optional[torch.Tensor] = None):
         return self.decode(self.diffuse(x, noise))
