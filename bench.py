@@ -48,7 +48,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region.  The sampler is started BEFORE the warm-up (nvidia-smi
+    takes a few hundred ms to produce its first row) and every row is stamped on arrival; ``mark()`` brackets the timed region
+    and ``stop()`` reports the rows inside it (or, for a region shorter than one sampling period, the rows nearest to it)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -57,11 +59,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,20 +73,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        if self.t0 is None:
+            self.t0 = time.monotonic()
+        else:
+            self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else time.monotonic()
+        inside = [r for ts, r in self.rows if t0 - 0.03 <= ts <= t1 + 0.08]
+        where = "timed region"
+        if not inside and self.rows:  # region shorter than a sampling period: the three rows nearest to it
+            mid = 0.5 * (t0 + t1)
+            inside = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            where = "nearest samples (timed region shorter than one sampling period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -93,7 +110,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 def synth_setup(name, B_total):
@@ -277,6 +294,9 @@ def main():
         out = eng.sample(x0, cond, tc, NS, 2.0, 1.0)
         return parallel.gather_streams(out, B * world)  # the single collective of the path (no-op at N = 1)
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
@@ -301,11 +321,10 @@ def main():
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         return float(tot.item()), per
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     l0 = eng.launch_count
+    clocks.mark()
     total_ms, per = timed(one_step, args.steps)
+    clocks.mark()
     launches = eng.launch_count - l0
     clk = clocks.stop() if rank == 0 else None
     value = NS * args.steps * world / (total_ms / 1e3)
