@@ -10,18 +10,22 @@ from after_b200 import _lib as L
 from after_b200 import config, synth
 from after_b200.streamer import MidiStreamer, Streamer
 from oracle import after_oracle as O
+from oracle import after_oracle_stream as S
 
 
 class OracleEngine:
     """Duck-typed ``Engine``: same attributes / methods the streamers use, computed by the oracle on CPU."""
 
-    def __init__(self, den_cfg, acfg, se_cfg, te_cfg, streaming=False, drop_value=-4.0):
+    def __init__(self, den_cfg, acfg, se_cfg, te_cfg, streaming=False, drop_value=-4.0, stream_slots=0):
         self.den_cfg, self.acfg, self.se_cfg, self.te_cfg = den_cfg, acfg, se_cfg, te_cfg
         self.device = torch.device("cpu")
         self.cfg = types.SimpleNamespace(tcond_dim=den_cfg.tcond_dim, cond_dim=den_cfg.cond_dim, n_channels=den_cfg.n_channels,
                                          drop_value=drop_value, max_cache_size=den_cfg.local_attention_size if streaming else 0)
         self.ae_ratio = acfg.ratio
-        self.stream_slots = 0  # offline codec / encoders (the streaming ones are covered by the -m gpu tests)
+        self.stream_slots = stream_slots  # > 0: the codec copies / structure encoder carry the exported model's state
+        self.codec_state = [dict() for _ in range(stream_slots)]
+        self.enc_state = [dict() for _ in range(stream_slots)]
+        self.stream_calls = []
         self.has_denoiser = self.has_codec = self.has_timbre = True
         self.has_structure = se_cfg is not None
         self.sd_den = synth.denoiser_state_dict(den_cfg, 1)
@@ -44,6 +48,18 @@ class OracleEngine:
     def structure_encode(self, z):
         return O.encoder1d_forward(self.sd_se, self.se_cfg, z)
 
+    def ae_encode_stream(self, slot, x):
+        self.stream_calls.append(("encode", slot))
+        return S.ae_encode_stream(self.sd_ae, self.acfg, self.codec_state[slot], x, gn_latent_frames=8)
+
+    def ae_decode_stream(self, slot, z):
+        self.stream_calls.append(("decode", slot))
+        return S.ae_decode_stream(self.sd_ae, self.acfg, self.codec_state[slot], z, gn_latent_frames=8)
+
+    def structure_encode_stream(self, slot, z):
+        self.stream_calls.append(("structure", slot))
+        return S.encoder1d_forward_stream(self.sd_se, self.se_cfg, self.enc_state[slot], z)
+
     def timbre_encode(self, z):
         return O.ecapa_forward(self.sd_te, self.te_cfg, z)
 
@@ -60,12 +76,12 @@ class OracleEngine:
 ACFG = config.small_autoencoder()  # ratio 128, 8 latent channels
 
 
-def small_engine(midi: bool, streaming: bool = False):
+def small_engine(midi: bool, streaming: bool = False, stream_slots: int = 0):
     den = config.DenoiserConfig(n_channels=ACFG.z_channels, embed_dim=256, n_layers=2, tcond_dim=128 if midi else 12,
                                 local_attention_size=16 if midi else 8)
     se = None if midi else config.Encoder1DConfig(in_size=ACFG.z_channels, channels=[16, 16, 12], ratios=[1, 1])
     te = config.EcapaConfig(in_size=ACFG.z_channels, channels=[32, 32, 32, 64], attention_channels=16, se_channels=16)
-    return OracleEngine(den, ACFG, se, te, streaming)
+    return OracleEngine(den, ACFG, se, te, streaming, stream_slots=stream_slots)
 
 
 def rel(a, b):
@@ -111,6 +127,28 @@ def test_streaming_engine_routes_to_sample_stream():
     b = st.diffuse(x, noise=torch.zeros(1, 8, 4))
     assert [c[0] for c in eng.calls] == ["sample_stream", "sample_stream"]
     assert rel(a, b) > 1e-4  # the second block attends to the first one's keys / values: state is carried
+
+
+def test_streamer_routes_the_two_codec_copies_like_the_export():
+    """export.py:161-168, 418-455: structure -> emb_model_structure.encode (slot 0) + encoder_time.forward_stream, timbre ->
+    emb_model_timbre.encode (slot 1), decode -> emb_model_structure.decode (slot 0); state is carried from buffer to buffer."""
+    eng = small_engine(midi=False, streaming=True, stream_slots=2)
+    st = Streamer(eng, n_signal_timbre=8)
+    st.set_nb_steps(1)
+    r = ACFG.ratio
+    g = torch.Generator().manual_seed(5)
+    audio = torch.rand(1, 2, 4 * r, generator=g) * 2 - 1
+    noise = torch.randn(1, 8, 4, generator=g)
+    a = st.forward(audio, noise=noise)
+    assert eng.stream_calls == [("encode", 0), ("structure", 0), ("encode", 1), ("decode", 0)]
+    b = st.forward(audio, noise=noise)
+    assert a.shape == b.shape == (1, 1, 4 * r)
+    assert rel(a, b) > 1e-3  # same buffer twice gives different audio: every stage carries state
+    midi = small_engine(midi=True, streaming=True, stream_slots=1)
+    ms = MidiStreamer(midi, n_poly=2, n_signal_timbre=8)
+    ms.timbre(torch.rand(1, 1, 4 * r, generator=g))
+    ms.decode(torch.randn(1, 8, 4, generator=g))
+    assert midi.stream_calls == [("encode", 0), ("decode", 0)]  # the MIDI export holds one codec copy (export_midi.py:165)
 
 
 def reference_piano_roll(notes, n_poly):
