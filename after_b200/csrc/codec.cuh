@@ -307,9 +307,6 @@ struct ConvNet {
   struct StreamCtx { int slot = 0; int dir = 0; bool convs = false; };
   const StreamCtx* sctx = nullptr;  // non-null while a streaming body runs
 
-  static constexpr size_t STREAM_SIMT_ROWS = 2048;
-  // stateless convs (kernel size 1) of a streaming call: same rule, decided per call
-  bool small_stream_call(int B, int T) const { return sctx != nullptr && (size_t)B * T <= STREAM_SIMT_ROWS; }
   static int stride_delay(int r_pad, int cd, int stride) { return (stride - ((r_pad + cd) % stride)) % stride; }
 
   // Register a conv for streaming.  (l, r): its padding; cd: cumulative delay in front of it (CachedConv1d.__init__).
@@ -323,10 +320,9 @@ struct ConvNet {
     StreamConv c;
     c.ns = ns; c.ns_al = ceil_div(ns, stride) * stride; c.in_phases = stride; c.t_scale = t_scale; c.Cp = L.w.Cin;
     c.slab = c.ns_al + stream_max_lat * t_scale;
-    // live buffers are a few hundred rows: a 256-row tcgen05 pair tile has ~10 us of fixed cost per launch (TMEM, barriers,
-    // cluster sync), the fp32 SIMT kernel about half of it -- and it is exact.  Decided once per engine (the cached state
-    // lives in ONE operand format): tensor cores only when a call can carry more than STREAM_SIMT_ROWS rows.
-    c.tc = tc_mode() && L.w.tc_ok && (size_t)maxB * stream_max_lat * t_scale > STREAM_SIMT_ROWS;
+    // (Tried: the fp32 SIMT kernel for live-sized buffers -- exact, but slower: 11.2 ms per Streamer.forward buffer with all
+    // convs on it, 7.8 ms with only the narrow layers, 7.1 ms with the tcgen05 kernel everywhere.)
+    c.tc = tc_mode() && L.w.tc_ok;
     c.w = L.w;
     TapTable t;
     t.ntaps = k;
@@ -474,7 +470,7 @@ struct ConvNet {
     if (a.norm == NORM_GROUP) AFTER_REQUIRE(xstats != nullptr, AFTER_ESTATE, "GroupNorm input has no statistics");
     ActOperand* dst = &op;
     int out_T = T, out_t0 = 0;
-    bool use_tc = tc_mode() && consumer.w.tc_ok && !small_stream_call(B, T);
+    bool use_tc = tc_mode() && consumer.w.tc_ok;
     if (sctx && sctx->convs && consumer.sid >= 0) {  // streaming conv: the new frames go behind its cached context
       const StreamConv& sc = sconv[consumer.sid];
       AFTER_REQUIRE(T <= sc.slab - sc.ns_al, AFTER_EINVAL, "streaming buffer longer than the state was sized for");
@@ -528,7 +524,7 @@ struct ConvNet {
                sc.ns_al / L.in_phases + T_rows);
       return;
     }
-    tap_gemm(op, B, T_rows, L.in_phases, L.w, e, small_stream_call(B, T_rows * L.in_phases) ? (int)AFTER_PRECISION_FP32_SIMT : precision, st);
+    tap_gemm(op, B, T_rows, L.in_phases, L.w, e, precision, st);
   }
 
   // ResnetBlock1d: block2(block1(x)) + skip(x)   (SimpleNetsStream.py:197-254).  x -> out (distinct buffers), y1 scratch.
