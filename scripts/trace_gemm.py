@@ -14,5 +14,4 @@ for (M, N, K) in shapes:
         A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
         eng.debug_gemm(A, W, b, prec)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 eng.close()
