@@ -615,6 +615,17 @@ struct Denoiser {
     net.proj = proj; net.kcache = kcache; net.vcache = vcache;
     net.cache_slab = cache_slab(); net.adaC_step_stride = (size_t)(B + 1) * L * 2 * D; net.barrier = stream_barrier;
     AFTER_CUDA_CHECK(cudaMemsetAsync(stream_barrier, 0, sizeof(unsigned), st));
+    net.dbg = nullptr;
+#ifdef AFTER_DEBUG
+    static unsigned long long* dbg = nullptr;   // AFTER_DEBUG_TRACE_STREAM=1: per-barrier timeline of CTA 0 (run with AFTER_NO_GRAPH=1)
+    static int trace = -1;
+    if (trace < 0) { const char* e = debug_env("AFTER_DEBUG_TRACE_STREAM"); trace = e ? atoi(e) : 0; }
+    if (trace > 0) {
+      if (!dbg) AFTER_CUDA_CHECK(cudaMalloc(&dbg, 256 * sizeof(unsigned long long)));
+      AFTER_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 256 * sizeof(unsigned long long), st));
+      net.dbg = dbg;
+    }
+#endif
     const size_t smem = (size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float);
     const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
     PdlScope pdl(false);  // plain launch: every CTA must become resident for the grid barrier, nothing to overlap with
@@ -624,6 +635,16 @@ struct Denoiser {
 #undef AFTER_LAUNCH_SS
     AFTER_COUNT_LAUNCH();
     last_N = 3 * B; last_T = T;
+#ifdef AFTER_DEBUG
+    if (net.dbg && --trace == 0) {
+      AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
+      std::vector<unsigned long long> hb(256);
+      AFTER_CUDA_CHECK(cudaMemcpy(hb.data(), net.dbg, 256 * 8, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "stream block trace of CTA 0 (ns): barrier k: [work before it] [wait in it]\n");
+      for (int k = 0; k < 60 && hb[2 * k]; ++k)
+        fprintf(stderr, "  %2d: work %6lld wait %6lld\n", k, k ? (long long)(hb[2 * k] - hb[2 * k - 1]) : 0LL, (long long)(hb[2 * k + 1] - hb[2 * k]));
+    }
+#endif
   }
 
   void sample_body(int B, int T, int nb_steps, cudaStream_t st, bool stream = false) {

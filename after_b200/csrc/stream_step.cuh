@@ -6,9 +6,13 @@
 // with programmatic dependent launch) a step costs ~266 us, i.e. ~9.5 us per kernel of launch / drain latency
 // (profiles/r01c_launches_stream_summary.txt).  Here one CTA per SM stays resident and the 27 phases of a step are
 // separated by a grid barrier (one atomic per CTA + a polled acquire load) instead of a kernel boundary.
-// Measured (base, B = 1, 4 frames, 8 steps): 2.15 ms as 28 launches per step -> 1.76 ms (221 us per step; the tiny model,
-// with a quarter of the weights, 156 us): what is left is ~6 us per phase of barrier + three dependent L2 round trips.
-// Tried and dropped: requesting a phase's first weights before the barrier (register spills at 512 threads, no gain).
+// Measured (base, B = 1, 4 frames, 8 steps): 2.15 ms as 28 launches per step -> 1.47 ms (184 us per step; the tiny model,
+// with a quarter of the weights, 139 us).  Per-barrier %globaltimer trace of CTA 0 (debug build,
+// AFTER_DEBUG_TRACE_STREAM): barrier wait 0.9-1.8 us, phase work A 5.3 / B 7-8 / C 3.6 / D 4.9 us.  What moved it from
+// 2.5 ms (first version) down: 512-thread CTAs, output columns interleaved over ALL CTAs (CTA-major numbering put the
+// 512 down-projection columns on 32 SMs), four 512-byte weight loads in flight per warp, operand rows fetched with
+// cp.async.bulk instead of a loop of per-thread loads, chunked in-place roll.  Tried and dropped: requesting a phase's
+// first weights before the barrier (register spills at 512 threads, no gain).
 //
 // Phases of a step (B = barrier):
 //   embed        h0[(b,t)] = GELU(W_in x + b_in)                                          (transformerv2.py:387-391)   B
@@ -42,12 +46,18 @@ struct StreamNetDev {
   size_t cache_slab;        // floats of KV history per diffusion step
   size_t adaC_step_stride;  // floats of the AdaLN-c table per diffusion step
   unsigned* barrier;        // zeroed before the launch
+  unsigned long long* dbg;  // -DAFTER_DEBUG builds: %globaltimer at every barrier entry / exit of CTA 0 (first 128 barriers)
 };
 
 constexpr int SS_MAXM = 16;
 
-__device__ __forceinline__ void ss_grid_sync(unsigned* ctr, unsigned& target, unsigned nb) {
+__device__ __forceinline__ void ss_grid_sync(unsigned* ctr, unsigned& target, unsigned nb, unsigned long long* dbg = nullptr) {
   __syncthreads();
+  if (kDebugBuild && dbg && blockIdx.x == 0 && threadIdx.x == 0 && target / nb < 128) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[2 * (target / nb)] = t;
+  }
   if (threadIdx.x == 0) {
     target += nb;
     __threadfence();
@@ -61,6 +71,11 @@ __device__ __forceinline__ void ss_grid_sync(unsigned* ctr, unsigned& target, un
         __trap();
       }
     } while (v < target);
+    if (kDebugBuild && dbg && blockIdx.x == 0 && target / nb <= 128) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[2 * (target / nb - 1) + 1] = t;
+    }
   }
   __syncthreads();
 }
@@ -69,7 +84,10 @@ __device__ __forceinline__ void ss_grid_sync(unsigned* ctr, unsigned& target, un
 __device__ __forceinline__ void ss_linear(const float* As, const float* __restrict__ Wm, const float* __restrict__ bias,
                                           const float* res, float* out, int ldo, int M, int N, int K, int gelu) {
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // column n -> CTA n % #CTAs, warp n / #CTAs: the columns (and their weight rows) are spread over ALL SMs first.  (With
+  // CTA-major numbering the 512 columns of the down projection landed on the first 32 CTAs, 16 each: 9.9 us per phase in the
+  // per-barrier trace of CTA 0 against 4.2 us for the up projection.)
+  const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int nw = gridDim.x * (blockDim.x >> 5);
   for (int n = gw; n < N; n += nw) {
     float acc[SS_MAXM];
@@ -112,10 +130,29 @@ __device__ __forceinline__ void ss_linear(const float* As, const float* __restri
   }
 }
 
-__device__ __forceinline__ void ss_load_rows(float* As, const float* __restrict__ A, int n) {
-  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
-    *reinterpret_cast<float4*>(As + i) = *reinterpret_cast<const float4*>(A + i);
-  __syncthreads();
+// Operand rows of a phase (up to 96 KB) into shared memory with ONE bulk copy per 16 KB against an mbarrier: a loop of
+// per-thread float4 loads paid one L2 round trip per iteration (9 iterations for the 74 KB of the down projection: ~4 us
+// of the 7 us that phase took in the per-barrier trace).
+__device__ __forceinline__ void ss_load_rows(float* As, const float* __restrict__ A, int n, uint64_t* bar, unsigned& parity) {
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+  __syncthreads();  // every warp is done with the previous contents of As
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)n * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(As);
+    const char* src = reinterpret_cast<const char*>(A);
+    for (uint32_t off = 0; off < bytes; off += 16384) {
+      const uint32_t sz = min(16384u, bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + off), "l"(src + off), "r"(sz), "r"(bar_s) : "memory");
+    }
+  }
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar_s), "r"(parity) : "memory");
+  }
+  parity ^= 1u;
 }
 
 // NT threads per CTA: 512 where the attention phase's registers allow it (MAXK <= 12), so that the 3 D / 3 x D output columns
@@ -127,6 +164,13 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
   constexpr int NV = D / 32;
   constexpr int NWARPS = NT / 32;
   extern __shared__ __align__(16) float ss_smem[];  // [M][max(D, HID)] operand rows; the attention phase uses its head
+  __shared__ __align__(8) uint64_t load_bar;
+  unsigned load_parity = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&load_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   pdl_wait();
   pdl_trigger();
   const int M = 3 * B * T;
@@ -157,7 +201,7 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
         net.h0[(size_t)r * D + d] = gelu_erf(acc);
       }
     }
-    ss_grid_sync(net.barrier, target, nb);
+    ss_grid_sync(net.barrier, target, nb, net.dbg);
 
     for (int l = 0; l < net.L; ++l) {
       const StreamLayerDev& ly = net.layer[l];
@@ -203,7 +247,7 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
       }
       __syncthreads();
       ss_linear(ss_smem, ly.qkv_w, nullptr, nullptr, qkv_l, 3 * D, M, 3 * D, D, 0);
-      ss_grid_sync(net.barrier, target, nb);
+      ss_grid_sync(net.barrier, target, nb, net.dbg);
 
       // ---- phase B: one CTA per token (warp = head, lane = dims (2 lane, 2 lane + 1) of it)
       for (int row = blockIdx.x; row < M; row += nb) {
@@ -305,23 +349,23 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
         }
         __syncthreads();
       }
-      ss_grid_sync(net.barrier, target, nb);
+      ss_grid_sync(net.barrier, target, nb, net.dbg);
 
       // ---- phase C: MLP up projection + GELU
-      ss_load_rows(ss_smem, net.sk_a, M * D);
+      ss_load_rows(ss_smem, net.sk_a, M * D, &load_bar, load_parity);
       ss_linear(ss_smem, ly.mlp0_w, ly.mlp0_b, nullptr, net.sk_hid, net.HID, M, net.HID, D, 1);
-      ss_grid_sync(net.barrier, target, nb);
+      ss_grid_sync(net.barrier, target, nb, net.dbg);
 
       // ---- phase D: MLP down projection + residual: reads hB, writes hA (the next layer's input)
-      ss_load_rows(ss_smem, net.sk_hid, M * net.HID);
+      ss_load_rows(ss_smem, net.sk_hid, M * net.HID, &load_bar, load_parity);
       ss_linear(ss_smem, ly.mlp2_w, ly.mlp2_b, net.hB, net.hA, D, M, D, net.HID, 0);
-      ss_grid_sync(net.barrier, target, nb);
+      ss_grid_sync(net.barrier, target, nb, net.dbg);
     }
 
     // ---- out projection
-    ss_load_rows(ss_smem, net.hA, M * D);
+    ss_load_rows(ss_smem, net.hA, M * D, &load_bar, load_parity);
     ss_linear(ss_smem, net.out_w, net.out_b, nullptr, net.proj, net.C, M, net.C, D, 0);
-    ss_grid_sync(net.barrier, target, nb);
+    ss_grid_sync(net.barrier, target, nb, net.dbg);
 
     // ---- CFG combine + Euler update (model.py:751-759, 777-783) and roll_cache(T, s) (transformerv2.py:167-186)
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = nb * blockDim.x;
@@ -358,7 +402,7 @@ stream_block_kernel(const __grid_constant__ StreamNetDev net, int B, int T, int 
         }
       }
     }
-    ss_grid_sync(net.barrier, target, nb);
+    ss_grid_sync(net.barrier, target, nb, net.dbg);
   }
 }
 
