@@ -171,7 +171,9 @@ struct Denoiser {
     h0 = arena->alloc<float>((size_t)maxRows * D);
     h = arena->alloc<float>((size_t)maxRows * D);
     h_part = arena->alloc<float>((size_t)maxRows * D);
-    qkv = arena->alloc<float>((size_t)maxRows * 3 * D);
+    // + 32 zeroed rows: attn_chunk_group_kernel reads up to MAXK - 1 rows past the last chunk (masked, must be finite)
+    qkv = arena->alloc<float>((size_t)(maxRows + 32) * 3 * D);
+    AFTER_CUDA_CHECK(cudaMemset(qkv, 0, (size_t)(maxRows + 32) * 3 * D * sizeof(float)));
     proj = arena->alloc<float>((size_t)maxRows * C);
     alloc_operand(a_op, *arena, (size_t)maxRows * D, tc_mode(), false);
     alloc_operand(hid_op, *arena, (size_t)maxRows * HID, tc_mode(), false);
@@ -315,6 +317,25 @@ struct Denoiser {
         static int staged = -1, qpw = -1;
         if (staged < 0) { const char* e = debug_env("AFTER_ATTN"); staged = (e && !strcmp(e, "staged")) ? 1 : 0; }
         if (qpw < 0) { const char* e = debug_env("AFTER_ATTN_QPW"); qpw = e ? atoi(e) : 4; }
+        // AFTER_ATTN: "warp" = the one-warp-per-chunk kernel, "g2" / "g4" = 2 / 4 chunks per block with all key rows in
+        // one batch (profiles/r02m..o_ab_attn_*.jsonl); default = the release configuration below
+        static int group = -1;
+        if (group < 0) {
+          const char* e = debug_env("AFTER_ATTN");
+          group = !e ? 1 : !strcmp(e, "warp") ? 0 : !strcmp(e, "g4") ? 4 : !strcmp(e, "g2") ? 2 : 1;
+        }
+        constexpr int KB0 = MAXK <= 12 ? MAXK : MAXK / 2;
+#define AFTER_LAUNCH_ATTN_GROUP(CPB, KB, MINB)                                                                            \
+  launch_k(attn_chunk_group_kernel<NH, MAXK, CPB, KB, MINB>, dim3(ceil_div((T + 3) / 4, CPB), n_seq),                     \
+           dim3(CPB * (NH / 2) * 32), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g,        \
+           layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride, flag_stride)
+        if (group == 1) {
+          AFTER_LAUNCH_ATTN_GROUP(8 / NH, KB0 / 2, 6);
+        } else if (group == 2) {
+          AFTER_LAUNCH_ATTN_GROUP(2, KB0, 512 / (NH * 32));
+        } else if (group == 4) {
+          AFTER_LAUNCH_ATTN_GROUP(4, KB0, 256 / (NH * 32));
+        } else
         if (staged && T % 16 == 0) {
           const size_t smem = 128 + (size_t)(16 + cfg.local_attention_size - 1) * 2 * D * sizeof(float);
           AFTER_LAUNCH_ATTN_WARP(true, 4, chunks / 4, smem);
@@ -323,8 +344,17 @@ struct Denoiser {
         } else if (qpw == 1) {
           AFTER_LAUNCH_ATTN_WARP(false, 1, chunks, 0);
         } else
+          AFTER_LAUNCH_ATTN_WARP(false, 4, ceil_div(chunks, 4), 0);
+#undef AFTER_LAUNCH_ATTN_GROUP
+#else
+        // NH / 2 warps per chunk, 128-thread blocks, key / value rows in two batches, 6 blocks (24 warps) per SM: the
+        // best of the variants measured (profiles/r02m..o_ab_attn_*.jsonl); the one-warp-per-chunk kernel stays in debug
+        // builds for A/B runs (AFTER_ATTN=warp)
+        launch_k(attn_chunk_group_kernel<NH, MAXK, 8 / NH, (MAXK <= 12 ? MAXK : MAXK / 2) / 2, 6>,
+                 dim3(ceil_div((T + 3) / 4, 8 / NH), n_seq), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
+                 seqmap(), layers[l].n3_g, layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride,
+                 flag_stride);
 #endif
-        AFTER_LAUNCH_ATTN_WARP(false, 4, ceil_div(chunks, 4), 0);
 #undef AFTER_LAUNCH_ATTN_WARP
         done = true;
       }

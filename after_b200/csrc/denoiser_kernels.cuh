@@ -14,14 +14,23 @@ struct RowOperandOut {
   __nv_bfloat16* lo = nullptr;
 };
 
+// hi/lo bf16 split of four values with the packed converter (2 cvt.rn.bf16x2 + 4 subtractions + 2 cvt instead of 8 scalar
+// conversions, 4 subtractions and 4 byte permutes): the row kernels are issue-bound once their loads are batched.
+__device__ __forceinline__ void split4_bf16_packed(const float4& x, uint2& hi, uint2& lo) {
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
+
 __device__ __forceinline__ void store_operand4(const RowOperandOut& o, size_t off, float4 v) {
   if (o.f32) *reinterpret_cast<float4*>(o.f32 + off) = v;
   if (o.hi) {
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(o.hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    if (o.lo) *reinterpret_cast<uint2*>(o.lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    uint2 hi, lo;
+    split4_bf16_packed(v, hi, lo);
+    *reinterpret_cast<uint2*>(o.hi + off) = hi;
+    if (o.lo) *reinterpret_cast<uint2*>(o.lo + off) = lo;
   }
 }
 
@@ -349,6 +358,227 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
         store_operand4(a_out, roff + 4 * LPH * i, ov);
       }
     }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Warp-group variant (the default for chunk size 4): NH / 2 warps per attention chunk, warp w owns the 128 feature
+// columns [128 w, +128) = heads 2w, 2w + 1, lane l the float4 at column 128 w + 4 l of EVERY row it touches (a warp reads
+// 512 contiguous bytes per row; a head is one half-warp).
+// Why: the one-warp-per-chunk kernel above keeps ~10 warps per SM resident and each walks ~30 dependent L2 round trips
+// (11 key rows, 11 value rows, queries, residual rows, one after the other because 4 float4 per lane and row leave no
+// registers to batch them): ncu shows 14 % warps active, 5 long-scoreboard stall cycles per issue, and the kernel lasts
+// exactly as long as one warp's chain (~23 us for 75 MB).  Here a lane holds ONE float4 per row, so all key rows of the
+// chunk are requested in one batch (<= 12 loads in flight per lane), then all value + residual rows: two round trips per
+// warp, four times as many warps.
+//   * scores: the 4 queries' partial dot products of a key are reduced over the 16 lanes of the head by a transposing
+//     butterfly (5 shuffles for 4 sums instead of 16); afterwards lane l holds the score of query (l >> 2) & 3 only, so the
+//     softmax state is MAXK registers per lane, not 4 MAXK; the probabilities travel back by 4 shuffles per key.
+//   * LayerNorm statistics span the NH / 2 warps of the chunk: per-warp partials of the 4 queries (6-shuffle transposing
+//     reduction) are exchanged through shared memory under a named barrier of the chunk's warps only (4 exchanges:
+//     mean / centred second moment of LN2, then of LN3 -- the same two-pass statistics as everywhere else).
+// Blocks hold CPB consecutive chunks so that the 7 history rows two neighbouring chunks share are L1 hits.
+// Key / value rows are read UNCONDITIONALLY for j < MAXK (one LDG with an immediate offset each, no predicate, no zero
+// fill): rows past the chunk end are masked in the softmax (their probability is exactly 0 and 0 * finite = 0), so they
+// only have to be readable and finite -- the next frames of the sequence, the next sequence, or the MAXK zeroed rows the
+// QKV buffer is padded with (Denoiser::finalize).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float head_reduce4(float a0, float a1, float a2, float a3) {
+  // Sums over the 16 lanes of a half-warp of four per-query partials held in LANE-PERMUTED order: a_i of lane l belongs
+  // to query i ^ rq(l), rq(l) = (l >> 2) & 3.  Partners across xor 8 (xor 4) hold the queries with bit 1 (bit 0) flipped in
+  // the same slot, so each lane always keeps slots 0, 1 (then 0) and sends slots 2, 3 (then 1): no selects.
+  // Result: the total of query rq(l), in every lane.
+  a0 += __shfl_xor_sync(0xffffffffu, a2, 8);
+  a1 += __shfl_xor_sync(0xffffffffu, a3, 8);
+  a0 += __shfl_xor_sync(0xffffffffu, a1, 4);
+  a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+  a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+  return a0;
+}
+__device__ __forceinline__ float warp_reduce4(float a0, float a1, float a2, float a3, int lane) {
+  // sums over the 32 lanes; result: the total of query lane >> 3, in every lane
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+  float k0 = b4 ? a2 : a0, k1 = b4 ? a3 : a1;
+  k0 += __shfl_xor_sync(0xffffffffu, b4 ? a0 : a2, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, b4 ? a1 : a3, 16);
+  float c = (b3 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// grid = (ceil(chunks per sequence / CPB), sequences); KB = key / value rows requested per batch, MINB = blocks per SM
+// the register allocation is held to.
+template <int NH, int MAXK, int CPB, int KB, int MINB>
+__global__ void __launch_bounds__(CPB * (NH / 2) * 32, MINB)
+attn_chunk_group_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
+                        const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
+                        const float* __restrict__ g3, const float* __restrict__ b3, int T, int window,
+                        int* zero_flags, int n_zero) {
+  constexpr int D = NH * 64;
+  constexpr int WPC = NH / 2;  // warps per chunk
+  static_assert(MAXK % KB == 0, "MAXK must split into equal batches");
+  __shared__ __align__(16) float red[CPB][2][2][WPC][4];  // [chunk][LayerNorm][mean | M2][warp][query]
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0 && blockIdx.y == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_flags[i] = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cib = warp / WPC, w = warp - cib * WPC;
+  const int c0 = (blockIdx.x * CPB + cib) * 4;
+  if (c0 >= T) return;  // whole warp groups leave: the named barriers below are per group
+  const int n = blockIdx.y;
+  const int ce = min(c0 + 4, T);
+  const int ks0 = max(0, c0 - window + 1);
+  const int nk = ce - ks0;  // <= MAXK
+  const int eoff = w * 128 + lane * 4;
+  const float* seq = qkv + (size_t)n * T * (3 * D) + eoff;
+  const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off + eoff;  // AdaLN-c row of this sequence (tail)
+  float* hrow = h + ((size_t)n * T + c0) * D + eoff;                          // row c0 + r: + r * D
+
+  // ---- queries (scaled into the log2 domain) and scores ------------------------------------------------------------
+  // q[i] of lane l is query i ^ rq(l) (see head_reduce4); ragged last chunk: surplus rows recompute the last one
+  const int rq = (lane >> 2) & 3;
+  float4 q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float4*>(seq + (size_t)min(c0 + (i ^ rq), T - 1) * (3 * D));
+  float sc[MAXK];
+  const float* kp = seq + (size_t)ks0 * (3 * D) + D;
+#pragma unroll
+  for (int b0 = 0; b0 < MAXK; b0 += KB) {
+    float4 kk[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      kk[j] = *reinterpret_cast<const float4*>(kp + (size_t)(b0 + j) * (3 * D));  // rows >= nk: see the header
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+      float a[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 t2 = __ffma2_rn(make_float2(q[r].x, q[r].y), make_float2(kk[j].x, kk[j].y),
+                                     __fmul2_rn(make_float2(q[r].z, q[r].w), make_float2(kk[j].z, kk[j].w)));
+        a[r] = t2.x + t2.y;
+      }
+      sc[b0 + j] = head_reduce4(a[0], a[1], a[2], a[3]);
+    }
+  }
+  // ---- softmax of this lane's query (scores scaled into the log2 domain inside the exponent's FMA) ----------------
+  // key ks0 + j is visible to query c0 + rq iff it is not older than the window (all keys of the chunk are visible):
+  // j >= jmin = min(c0, max(0, c0 + rq - window + 1)) - ks0
+  const int jmin = min(c0, max(0, c0 + rq - window + 1)) - ks0;
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    sc[j] = (j < nk && j >= jmin) ? sc[j] : -INFINITY;
+    m = fmaxf(m, sc[j]);
+  }
+  const float qs = 0.125f * 1.4426950408889634f;  // 1 / sqrt(64) * log2(e)
+  const float mqs = -m * qs;
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    sc[j] = ex2_approx(fmaf(sc[j], qs, mqs));  // 2^(-inf) = 0 for masked keys
+    l += sc[j];
+  }
+  l = rcp_approx(l);
+  // ---- P.V ----------------------------------------------------------------------------------------------------------
+  const int hb = lane & 16;
+  float4 o[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* vp = kp + D;
+  float4 res[4], al, be, gg, bb;
+#pragma unroll
+  for (int b0 = 0; b0 < MAXK; b0 += KB) {
+    float4 vv[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      vv[j] = *reinterpret_cast<const float4*>(vp + (size_t)(b0 + j) * (3 * D));
+    if (b0 + KB >= MAXK) {
+      // everything the tail needs is requested together with the last value rows: one more round trip saved
+#pragma unroll
+      for (int r = 0; r < 4; ++r) res[r] = *reinterpret_cast<const float4*>(hrow + (size_t)min(r, T - 1 - c0) * D);
+      al = *reinterpret_cast<const float4*>(ap);
+      be = *reinterpret_cast<const float4*>(ap + D);
+      gg = *reinterpret_cast<const float4*>(g3 + eoff);
+      bb = *reinterpret_cast<const float4*>(b3 + eoff);
+    }
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float p = __shfl_sync(0xffffffffu, sc[b0 + j], hb + 4 * r);
+        const float2 pp = make_float2(p, p);
+        const float2 a = __ffma2_rn(pp, make_float2(vv[j].x, vv[j].y), make_float2(o[r].x, o[r].y));
+        const float2 b = __ffma2_rn(pp, make_float2(vv[j].z, vv[j].w), make_float2(o[r].z, o[r].w));
+        o[r] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    }
+  }
+  // ---- residual, LayerNorm -> AdaLN-c -> h ; LayerNorm(affine) -> operand ------------------------------------------
+  float4 x[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float inv = __shfl_sync(0xffffffffu, l, hb + 4 * r);
+    x[r] = make_float4(fmaf(o[r].x, inv, res[r].x), fmaf(o[r].y, inv, res[r].y), fmaf(o[r].z, inv, res[r].z),
+                       fmaf(o[r].w, inv, res[r].w));
+  }
+  // LayerNorm statistics of the 4 query rows over the chunk's WPC warps with ONE exchange per norm: every warp reduces
+  // its 128 columns to (sum, sum of squares); var = E[x^2] - mean^2 (biased, as nn.LayerNorm).  The rows are O(1) with
+  // |mean| <~ std here (outputs of an AdaLN), so the one-pass form costs ~1e-7 relative, far inside the 1e-3 budget.
+  auto hsum = [](const float4& v) { return (v.x + v.y) + (v.z + v.w); };
+  auto hsq = [](const float4& v) { return fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))); };
+  auto group_stats = [&](int which, float (&mean)[4], float (&rstd)[4]) {
+    const float s1 = warp_reduce4(hsum(x[0]), hsum(x[1]), hsum(x[2]), hsum(x[3]), lane);
+    const float s2 = warp_reduce4(hsq(x[0]), hsq(x[1]), hsq(x[2]), hsq(x[3]), lane);
+    if ((lane & 7) == 0) {  // the lane holds the totals of query lane >> 3
+      red[cib][which][0][w][lane >> 3] = s1;
+      red[cib][which][1][w][lane >> 3] = s2;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(cib + 1), "r"(WPC * 32) : "memory");
+    float4 t1 = *reinterpret_cast<const float4*>(&red[cib][which][0][0][0]);
+    float4 t2 = *reinterpret_cast<const float4*>(&red[cib][which][1][0][0]);
+#pragma unroll
+    for (int i = 1; i < WPC; ++i) {
+      const float4 p1 = *reinterpret_cast<const float4*>(&red[cib][which][0][i][0]);
+      const float4 p2 = *reinterpret_cast<const float4*>(&red[cib][which][1][i][0]);
+      t1.x += p1.x; t1.y += p1.y; t1.z += p1.z; t1.w += p1.w;
+      t2.x += p2.x; t2.y += p2.y; t2.z += p2.z; t2.w += p2.w;
+    }
+    const float a1[4] = {t1.x, t1.y, t1.z, t1.w}, a2[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      mean[r] = a1[r] * (1.0f / (float)D);
+      rstd[r] = rsqrt_approx(fmaf(a2[r], 1.0f / (float)D, fmaf(-mean[r], mean[r], 1e-5f)));
+    }
+  };
+  float mean[4], rstd[4];
+  group_stats(0, mean, rstd);
+  const float4 al1 = make_float4(1.f + al.x, 1.f + al.y, 1.f + al.z, 1.f + al.w);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    x[r].x = (x[r].x - mean[r]) * rstd[r] * al1.x + be.x;
+    x[r].y = (x[r].y - mean[r]) * rstd[r] * al1.y + be.y;
+    x[r].z = (x[r].z - mean[r]) * rstd[r] * al1.z + be.z;
+    x[r].w = (x[r].w - mean[r]) * rstd[r] * al1.w + be.w;
+    if (c0 + r < T) *reinterpret_cast<float4*>(hrow + (size_t)r * D) = x[r];
+  }
+  group_stats(1, mean, rstd);
+  const size_t ooff = ((size_t)n * T + c0) * D + eoff;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float4 ov;
+    ov.x = (x[r].x - mean[r]) * rstd[r] * gg.x + bb.x;
+    ov.y = (x[r].y - mean[r]) * rstd[r] * gg.y + bb.y;
+    ov.z = (x[r].z - mean[r]) * rstd[r] * gg.z + bb.z;
+    ov.w = (x[r].w - mean[r]) * rstd[r] * gg.w + bb.w;
+    if (c0 + r < T) store_operand4(a_out, ooff + (size_t)r * D, ov);
   }
 }
 
