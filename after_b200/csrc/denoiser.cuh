@@ -44,6 +44,7 @@ struct Denoiser {
   // workspace
   float *x_state, *x_in, *cond_buf, *tc_buf, *time_buf;
   float *h0, *h, *qkv, *proj;
+  __nv_bfloat16* qkv_bf = nullptr;  // bf16 mode: the QKV buffer the attention kernel reads (half the epilogue / attention bytes)
   float* h_part = nullptr;  // second K half of a K-split down projection (added by the next layer's AdaLN-t kernel)
   ActOperand a_op, hid_op;  // GEMM A operands: LN output [rows, D], MLP hidden [rows, HID]
   float *tcemb, *adaT, *E, *F1, *feat, *adaC;
@@ -174,6 +175,10 @@ struct Denoiser {
     // + 32 zeroed rows: attn_chunk_group_kernel reads up to MAXK - 1 rows past the last chunk (masked, must be finite)
     qkv = arena->alloc<float>((size_t)(maxRows + 32) * 3 * D);
     AFTER_CUDA_CHECK(cudaMemset(qkv, 0, (size_t)(maxRows + 32) * 3 * D * sizeof(float)));
+    if (precision == AFTER_PRECISION_BF16) {
+      qkv_bf = arena->alloc<__nv_bfloat16>((size_t)(maxRows + 32) * 3 * D);
+      AFTER_CUDA_CHECK(cudaMemset(qkv_bf, 0, (size_t)(maxRows + 32) * 3 * D * sizeof(__nv_bfloat16)));
+    }
     proj = arena->alloc<float>((size_t)maxRows * C);
     alloc_operand(a_op, *arena, (size_t)maxRows * D, tc_mode(), false);
     alloc_operand(hid_op, *arena, (size_t)maxRows * HID, tc_mode(), false);
@@ -237,6 +242,14 @@ struct Denoiser {
 
   // ------------------------------------------------------------------ building blocks
   SeqMap seqmap() const { return SeqMap{map_src, map_trow, map_tstride, map_crow}; }
+  // bf16 mode, offline attention by attn_chunk_group_kernel (chunk 4, band <= 20) behind the 256-wide CTA-pair QKV GEMM:
+  // q | k | v are written and read as bf16 (AFTER_QKV_BF16=0 in debug builds keeps the fp32 buffer for A/B runs)
+  bool qkv_bf16_ok(int l) const {
+    static int off = -1;
+    if (off < 0) { const char* e = debug_env("AFTER_QKV_BF16"); off = (e && e[0] == '0') ? 1 : 0; }
+    return !off && qkv_bf != nullptr && cfg.attention_chunk_size == 4 && cfg.attention_chunk_size + cfg.local_attention_size - 1 <= 20 &&
+           layers[l].qkv.tc2_ok && layers[l].qkv.bn2 == 256 && use_pair_kernel();
+  }
 
   void gemm(const GemmWeight& w, ActOperand& a, int nseq, int T, const GemmEpi& epi, cudaStream_t st) {
     tap_gemm(a, nseq, T, 1, w, epi, precision, st);
@@ -326,10 +339,14 @@ struct Denoiser {
         }
         constexpr int KB0 = MAXK <= 12 ? MAXK : MAXK / 2;
 #define AFTER_LAUNCH_ATTN_GROUP(CPB, KB, MINB)                                                                            \
-  launch_k(attn_chunk_group_kernel<NH, MAXK, CPB, KB, MINB>, dim3(ceil_div((T + 3) / 4, CPB), n_seq),                     \
+  launch_k(attn_chunk_group_kernel<NH, MAXK, CPB, KB, MINB, float>, dim3(ceil_div((T + 3) / 4, CPB), n_seq),              \
            dim3(CPB * (NH / 2) * 32), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g,        \
            layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride, flag_stride)
-        if (group == 1) {
+        if (group == 1 && qkv_bf16_ok(l)) {
+          launch_k(attn_chunk_group_kernel<NH, MAXK, 8 / NH, KB0 / 2, 6, __nv_bfloat16>, dim3(ceil_div((T + 3) / 4, 8 / NH), n_seq),
+                   dim3(128), 0, st, qkv_bf, h, o, adaC_step, L * 2 * D, l * 2 * D, seqmap(), layers[l].n3_g, layers[l].n3_b, T,
+                   cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride, flag_stride);
+        } else if (group == 1) {
           AFTER_LAUNCH_ATTN_GROUP(8 / NH, KB0 / 2, 6);
         } else if (group == 2) {
           AFTER_LAUNCH_ATTN_GROUP(2, KB0, 512 / (NH * 32));
@@ -350,10 +367,16 @@ struct Denoiser {
         // NH / 2 warps per chunk, 128-thread blocks, key / value rows in two batches, 6 blocks (24 warps) per SM: the
         // best of the variants measured (profiles/r02m..o_ab_attn_*.jsonl); the one-warp-per-chunk kernel stays in debug
         // builds for A/B runs (AFTER_ATTN=warp)
-        launch_k(attn_chunk_group_kernel<NH, MAXK, 8 / NH, (MAXK <= 12 ? MAXK : MAXK / 2) / 2, 6>,
-                 dim3(ceil_div((T + 3) / 4, 8 / NH), n_seq), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
-                 seqmap(), layers[l].n3_g, layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride,
-                 flag_stride);
+        if (qkv_bf16_ok(l))
+          launch_k(attn_chunk_group_kernel<NH, MAXK, 8 / NH, (MAXK <= 12 ? MAXK : MAXK / 2) / 2, 6, __nv_bfloat16>,
+                   dim3(ceil_div((T + 3) / 4, 8 / NH), n_seq), dim3(128), 0, st, qkv_bf, h, o, adaC_step, L * 2 * D, l * 2 * D,
+                   seqmap(), layers[l].n3_g, layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride,
+                   flag_stride);
+        else
+          launch_k(attn_chunk_group_kernel<NH, MAXK, 8 / NH, (MAXK <= 12 ? MAXK : MAXK / 2) / 2, 6, float>,
+                   dim3(ceil_div((T + 3) / 4, 8 / NH), n_seq), dim3(128), 0, st, qkv, h, o, adaC_step, L * 2 * D, l * 2 * D,
+                   seqmap(), layers[l].n3_g, layers[l].n3_b, T, cfg.local_attention_size, mlp_flags + (size_t)l * flag_stride,
+                   flag_stride);
 #endif
 #undef AFTER_LAUNCH_ATTN_WARP
         done = true;
@@ -458,7 +481,9 @@ struct Denoiser {
       else launch_adaln_t<8>(hin, hadd, l == 0, l, rows, T, st);
       part = false;
       if (cache_index < 0) {
-        GemmEpi e; e.out_f32 = qkv; e.ldo = 3 * D; e.rope = 1; e.D = D; e.rot_half = 16; e.rope_tab = rope_tab;
+        GemmEpi e; e.ldo = 3 * D; e.rope = 1; e.D = D; e.rot_half = 16; e.rope_tab = rope_tab;
+        if (qkv_bf16_ok(l)) e.out_hi = qkv_bf;
+        else e.out_f32 = qkv;
         gemm(layers[l].qkv, a_op, N, T, e, st);
         attn(l, adaC_step, rows, T, st);
       } else {  // keys are cached un-rotated: plain epilogue into this layer's slot, rotation inside the attention kernel

@@ -408,6 +408,15 @@ __device__ __forceinline__ float warp_reduce4(float a0, float a1, float a2, floa
   return c;
 }
 
+// four consecutive QKV elements: fp32 rows, or the bf16 rows the bf16 mode's QKV epilogue writes (EPI_ROPE_BF16)
+__device__ __forceinline__ float4 load_qkv4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_qkv4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -416,9 +425,9 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 
 // grid = (ceil(chunks per sequence / CPB), sequences); KB = key / value rows requested per batch, MINB = blocks per SM
 // the register allocation is held to.
-template <int NH, int MAXK, int CPB, int KB, int MINB>
+template <int NH, int MAXK, int CPB, int KB, int MINB, typename QT>
 __global__ void __launch_bounds__(CPB * (NH / 2) * 32, MINB)
-attn_chunk_group_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_out,
+attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_out,
                         const float* __restrict__ adaC, int ada_ld, int ada_off, SeqMap map,
                         const float* __restrict__ g3, const float* __restrict__ b3, int T, int window,
                         int* zero_flags, int n_zero) {
@@ -438,7 +447,7 @@ attn_chunk_group_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
   const int ks0 = max(0, c0 - window + 1);
   const int nk = ce - ks0;  // <= MAXK
   const int eoff = w * 128 + lane * 4;
-  const float* seq = qkv + (size_t)n * T * (3 * D) + eoff;
+  const QT* seq = qkv + (size_t)n * T * (3 * D) + eoff;
   const float* ap = adaC + (size_t)map.c_row[n] * ada_ld + ada_off + eoff;  // AdaLN-c row of this sequence (tail)
   float* hrow = h + ((size_t)n * T + c0) * D + eoff;                          // row c0 + r: + r * D
 
@@ -447,15 +456,15 @@ attn_chunk_group_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
   const int rq = (lane >> 2) & 3;
   float4 q[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float4*>(seq + (size_t)min(c0 + (i ^ rq), T - 1) * (3 * D));
+  for (int i = 0; i < 4; ++i) q[i] = load_qkv4(seq + (size_t)min(c0 + (i ^ rq), T - 1) * (3 * D));
   float sc[MAXK];
-  const float* kp = seq + (size_t)ks0 * (3 * D) + D;
+  const QT* kp = seq + (size_t)ks0 * (3 * D) + D;
 #pragma unroll
   for (int b0 = 0; b0 < MAXK; b0 += KB) {
     float4 kk[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j)
-      kk[j] = *reinterpret_cast<const float4*>(kp + (size_t)(b0 + j) * (3 * D));  // rows >= nk: see the header
+      kk[j] = load_qkv4(kp + (size_t)(b0 + j) * (3 * D));  // rows >= nk: see the header
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
       float a[4];
@@ -492,14 +501,14 @@ attn_chunk_group_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a
   float4 o[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* vp = kp + D;
+  const QT* vp = kp + D;
   float4 res[4], al, be, gg, bb;
 #pragma unroll
   for (int b0 = 0; b0 < MAXK; b0 += KB) {
     float4 vv[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j)
-      vv[j] = *reinterpret_cast<const float4*>(vp + (size_t)(b0 + j) * (3 * D));
+      vv[j] = load_qkv4(vp + (size_t)(b0 + j) * (3 * D));
     if (b0 + KB >= MAXK) {
       // everything the tail needs is requested together with the last value rows: one more round trip saved
 #pragma unroll

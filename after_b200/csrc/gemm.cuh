@@ -355,7 +355,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   EPI_PLAIN : (+bias) (+residual) -> fp32 (and/or bf16 hi/lo), optional GroupNorm statistics
 //   EPI_ROPE  : rotary embedding on the q / k thirds -> fp32                       (QKV projection, no bias)
 //   EPI_GELU  : +bias, exact GELU -> bf16 hi/lo (and/or fp32)                      (MLP up-projection)
-enum EpiMode { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_GELU = 2 };
+//   EPI_ROPE_BF16 : EPI_ROPE with a bf16 result (out_hi): the QKV buffer of the bf16 mode -- the GEMM epilogues run at
+//               the chip's write bandwidth (profiles/EXPERIMENTS.md), so half the bytes is half the epilogue
+enum EpiMode { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_GELU = 2, EPI_ROPE_BF16 = 3 };
+__host__ __device__ constexpr bool epi_is_rope(int mode) { return mode == EPI_ROPE || mode == EPI_ROPE_BF16; }
 
 // Global operands of one half-block's epilogue (residual rows or RoPE cos/sin rows), requested before the TMEM load.
 // Half-block = 32 frames x 16 columns; transposed ownership: lane -> 4 consecutive columns (lane & 3) * 4 of rows
@@ -378,7 +381,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi& e, EpiAux& aux, int 
         p += step;
       }
     }
-  } else if (MODE == EPI_ROPE) {
+  } else if (epi_is_rope(MODE)) {
     const bool rot = (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
     if (rot) {
       const float2* p = e.rope_tab + (size_t)(t_base + rsub) * e.rot_half + ((col & 63) >> 1);
@@ -424,7 +427,7 @@ __device__ __forceinline__ void epi_block(const GemmEpi& e, float* stg, const ui
   const int rsub = lane >> 2;
   const int col = col0 + cq * 4;
   const int nvalid = T - t_base;
-  const bool rot = MODE == EPI_ROPE && (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
+  const bool rot = epi_is_rope(MODE) && (col0 / e.D) < 2 && (col0 & 63) < 2 * e.rot_half;  // warp-uniform
   const bool has_res = MODE == EPI_PLAIN && e.res != nullptr;
   const size_t off0 = ((size_t)b * T + t_base + rsub) * e.ldo + col;
   const size_t step = (size_t)8 * e.ldo;
@@ -932,7 +935,7 @@ tap_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           uint32_t v[16];
           tmem_ld16_issue(taddr + c, v);
           tmem_ld_wait();
-          constexpr int OUTS = MODE == EPI_ROPE ? 1 : -1;  // the RoPE flavour only ever writes the fp32 QKV buffer
+          constexpr int OUTS = MODE == EPI_ROPE ? 1 : MODE == EPI_ROPE_BF16 ? 2 : -1;  // the RoPE flavours write the fp32 / the bf16 QKV buffer only
           if (T - t_base >= 32) epi_block<MODE, OUTS, true>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
           else epi_block<MODE, OUTS, false>(epi, stg, v, aux, bias4, b, t_base, T, n0 + c, lane);
         }

@@ -93,9 +93,11 @@ struct GemmWeight {
   bool tc2_ok = false;
 };
 
-inline int pick_bn2(int N, int n_per_phase) {
+inline int pick_bn2(int N, int n_per_phase, int cap = 256) {
+  static int env_cap = -1;  // AFTER_BN2_CAP (debug builds): widest CTA-pair tile for every weight, for A/B runs
+  if (env_cap < 0) { const char* e = debug_env("AFTER_BN2_CAP"); env_cap = e ? atoi(e) : 256; }
   for (int bn : {256, 128, 64})
-    if (N % bn == 0 && (n_per_phase == 0 || n_per_phase % bn == 0)) return bn;
+    if (bn <= cap && bn <= env_cap && N % bn == 0 && (n_per_phase == 0 || n_per_phase % bn == 0)) return bn;
   return 0;
 }
 inline bool use_pair_kernel() {
@@ -250,6 +252,7 @@ inline void tc_init_kernels() {
   set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_ROPE>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));  \
   set((const void*)tc::tap_gemm_tc2_kernel<BN, tc::EPI_GELU>, std::max(tc::Smem2<BN>::total(3), tc::Smem2<BN>::total(1)));
   AFTER_SET_TC2(256)
+  set((const void*)tc::tap_gemm_tc2_kernel<256, tc::EPI_ROPE_BF16>, std::max(tc::Smem2<256>::total(3), tc::Smem2<256>::total(1)));
   set((const void*)tc::mlp_fused_tc2_kernel<256>, std::max(tc::Smem2<256>::total(3), tc::Smem2<256>::total(1)));
   AFTER_SET_TC2(128)
   AFTER_SET_TC2(64)
@@ -402,7 +405,9 @@ inline void tap_gemm(ActOperand& A, int B, int T, int P, const GemmWeight& W, Ge
     else if (W.bn2 == 128) launch_tap_gemm_tc2_bn<128, MODE>(am, W, epi, B, T, nprod, st);      \
     else launch_tap_gemm_tc2_bn<64, MODE>(am, W, epi, B, T, nprod, st);                         \
   } while (0)
-      if (epi.rope) AFTER_LAUNCH_TC2(tc::EPI_ROPE);
+      if (epi.rope && epi.out_hi && !epi.out_f32 && !epi.out_lo && W.bn2 == 256)
+        launch_tap_gemm_tc2_bn<256, tc::EPI_ROPE_BF16>(am, W, epi, B, T, nprod, st);
+      else if (epi.rope) AFTER_LAUNCH_TC2(tc::EPI_ROPE);
       else if (epi.gelu) AFTER_LAUNCH_TC2(tc::EPI_GELU);
       else AFTER_LAUNCH_TC2(tc::EPI_PLAIN);
 #undef AFTER_LAUNCH_TC2
