@@ -220,7 +220,8 @@ struct Denoiser {
       AFTER_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel<SKINNY_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float))));
       stream_barrier = arena->alloc<unsigned>(4);
-      const int ss_bytes = (int)((size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float));
+      // operand rows + the LayerNorm parameters of every layer (stream_block_kernel keeps them in shared memory)
+      const int ss_bytes = (int)(((size_t)SKINNY_ROWS * std::max(D, HID) + (size_t)L * 4 * D) * sizeof(float));
       AFTER_REQUIRE(ss_bytes <= 200 * 1024, AFTER_EINVAL, "embed_dim * mlp_multiplier too large for the streaming kernels");
       auto set_ss = [&](const void* f) { AFTER_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ss_bytes)); };
       set_ss((const void*)stream_block_kernel<8, 12, 512>); set_ss((const void*)stream_block_kernel<8, 20, 256>); set_ss((const void*)stream_block_kernel<8, 32, 256>);
@@ -654,7 +655,8 @@ struct Denoiser {
   bool persistent_stream_ok(int B, int T) const {
     static int off = -1;
     if (off < 0) { const char* e = debug_env("AFTER_STREAM_PERSISTENT"); off = (e && e[0] == '0') ? 1 : 0; }
-    return !off && !g_prof.on && cacheW > 0 && sk_a != nullptr && 3 * B * T <= SKINNY_ROWS && L <= 8 && n_sms > 0 && D % 128 == 0;
+    return !off && !g_prof.on && cacheW > 0 && sk_a != nullptr && 3 * B * T <= SKINNY_ROWS && L <= 8 && n_sms > 0 && D % 128 == 0 &&
+           HID <= 1536;  // stream_block_kernel's K-quartered down projection holds 3 x 128 weights of a quarter per lane
   }
   void stream_block_persistent(int B, int T, int nb_steps, cudaStream_t st) {
     StreamNetDev net{};
@@ -681,7 +683,7 @@ struct Denoiser {
       net.dbg = dbg;
     }
 #endif
-    const size_t smem = (size_t)SKINNY_ROWS * std::max(D, HID) * sizeof(float);
+    const size_t smem = ((size_t)SKINNY_ROWS * std::max(D, HID) + (size_t)L * 4 * D) * sizeof(float);
     const int mk = cfg.attention_chunk_size + cfg.local_attention_size - 1;
     PdlScope pdl(false);  // plain launch: every CTA must become resident for the grid barrier, nothing to overlap with
 #define AFTER_LAUNCH_SS(NH, MK, NT) launch_k(stream_block_kernel<NH, MK, NT>, dim3(n_sms), dim3(NT), smem, st, net, B, T, nb_steps)
