@@ -379,9 +379,9 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
 //     mean / centred second moment of LN2, then of LN3 -- the same two-pass statistics as everywhere else).
 // Blocks hold CPB consecutive chunks so that the 7 history rows two neighbouring chunks share are L1 hits.
 // Key / value rows are read UNCONDITIONALLY for j < MAXK (one LDG with an immediate offset each, no predicate, no zero
-// fill): rows past the chunk end are masked in the softmax (their probability is exactly 0 and 0 * finite = 0), so they
-// only have to be readable and finite -- the next frames of the sequence, the next sequence, or the MAXK zeroed rows the
-// QKV buffer is padded with (Denoiser::finalize).
+// fill): rows past the chunk end are masked in the softmax and skipped in P.V (a warp-uniform test), so they only have to
+// be readable -- the next frames of the sequence, the next sequence, or the 32 pad rows behind the QKV buffer
+// (Denoiser::finalize).
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float head_reduce4(float a0, float a1, float a2, float a3) {
   // Sums over the 16 lanes of a half-warp of four per-query partials held in LANE-PERMUTED order: a_i of lane l belongs
@@ -520,6 +520,7 @@ attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_ou
     }
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
+      if (b0 + j >= nk) continue;  // warp-uniform; stale rows past the chunk end may hold anything (0 * inf is not 0)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float p = __shfl_sync(0xffffffffu, sc[b0 + j], hb + 4 * r);

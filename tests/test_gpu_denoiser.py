@@ -222,3 +222,24 @@ def test_engine_from_run_folder(tmp_path):
         assert rel(got, O.sample(den, mc.denoiser, x0, cond, tc, 3, 2.0, 1.0)) < TOL["fp32"]
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stale_rows_behind_a_smaller_batch_do_not_leak(precision):
+    """attn_chunk_group_kernel reads key / value rows past the last chunk unconditionally (masked afterwards).  Rows behind
+    the live batch may hold anything -- here the non-finite q|k|v a NaN input left there -- and must not reach the result."""
+    frames = 22  # ragged: the last chunk has 2 queries and reads 2 + 8 rows of the next sequence / the stale area
+    eng, sd, mc = make_engine("base", 5, precision, frames, max_batch=2, max_steps=2)
+    fresh, _, _ = make_engine("base", 5, precision, frames, max_batch=2, max_steps=2)
+    try:
+        x0, cond, tc = (t.cuda() for t in synth.synth_inputs(2, mc.denoiser, frames=frames))
+        bad = torch.full_like(x0, float("nan"))
+        poisoned = eng.sample(bad, cond, tc, 2, 2.0, 1.0)
+        assert not torch.isfinite(poisoned).all()
+        out = eng.sample(x0[:1].contiguous(), cond[:1].contiguous(), tc[:1].contiguous(), 2, 2.0, 1.0)
+        ref = fresh.sample(x0[:1].contiguous(), cond[:1].contiguous(), tc[:1].contiguous(), 2, 2.0, 1.0)
+        assert torch.isfinite(out).all()
+        assert torch.equal(out, ref)
+    finally:
+        eng.close()
+        fresh.close()
