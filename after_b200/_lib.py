@@ -17,6 +17,7 @@ PRECISION_FP32, PRECISION_BF16, PRECISION_FP32_SIMT = 0, 1, 2
 PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_simt": PRECISION_FP32_SIMT}
 DTYPE_F32, DTYPE_F64, DTYPE_I64 = 0, 1, 2
 MODULE_DENOISER, MODULE_AUTOENCODER, MODULE_STRUCTURE_ENCODER, MODULE_TIMBRE_ENCODER, MODULE_UNET = 0, 1, 2, 3, 4
+MODULE_LATENT_MAP = 5
 CFG_AUDIO, CFG_MIDI = 0, 1
 KERNEL_CLASSES = {"tap_gemm_tc": 0, "tap_gemm_simt": 1, "attention": 2, "row_norm": 3, "act_operand": 4, "pqmf": 5,
                   "mlp_fused": 7}
@@ -125,6 +126,7 @@ PROTOTYPES = {
     "after_stream_reset": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "after_structure_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "after_timbre_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "after_latent_map": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "after_generate": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float,
                                  C.c_float, C.c_void_p]),
     "after_generate_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,

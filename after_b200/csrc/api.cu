@@ -8,6 +8,7 @@
 #include "context.cuh"
 #include "denoiser.cuh"
 #include "ecapa.cuh"
+#include "latent_map.cuh"
 #include "unet.cuh"
 
 namespace after {
@@ -21,7 +22,7 @@ struct after_ctx {
   after_config cfg{};
   int device = 0;
   int precision = -1;  // -1: weights not finalized
-  TensorMap tensors[5];
+  TensorMap tensors[6];
   Arena arena;
   StreamBridge bridge;
   Denoiser denoiser;
@@ -29,6 +30,7 @@ struct after_ctx {
   StructureEncoder structure;
   TimbreEncoder timbre;
   UNet unet;
+  LatentMap latent_map;
   bool have_codec = false, have_structure = false, have_timbre = false, have_unet = false;
   bool net_is_unet() const { return have_unet && denoiser.D == 0; }
   // device staging of the *_host entry points (the copies go straight from / to the caller's host pointers)
@@ -175,7 +177,7 @@ int after_load_tensor(after_handle h, int module, const char* key, const void* d
   int ignored = 0;
   int rc = guarded(h, [&] {
     AFTER_REQUIRE(h->precision < 0, AFTER_ESTATE, "weights already finalized");
-    AFTER_REQUIRE(module >= 0 && module < 5, AFTER_EINVAL, "unknown module id");
+    AFTER_REQUIRE(module >= 0 && module < 6, AFTER_EINVAL, "unknown module id");
     AFTER_REQUIRE(key && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 8, AFTER_EINVAL, "bad tensor arguments");
     const std::string k(key);
     // buffers the offline path never reads: streaming caches, unused position table, GroupNorm stream pads
@@ -236,6 +238,7 @@ int after_finalize_weights(after_handle h, int precision) {
       h->have_unet = true;
       any = true;
     }
+    if (!h->tensors[AFTER_MODULE_LATENT_MAP].empty()) h->latent_map.finalize(h->tensors[AFTER_MODULE_LATENT_MAP], &h->arena);
     AFTER_REQUIRE(any, AFTER_EMISSING, "no tensors were loaded");
     for (auto& m : h->tensors) m.clear();  // host copies are no longer needed
     h->precision = precision;
@@ -464,6 +467,16 @@ int after_timbre_encode(after_handle h, const float* z, float* cond, int B, int 
     AFTER_REQUIRE(z && cond, AFTER_EINVAL, "null tensor pointer");
     BridgeScope bridge(h->bridge, stream);
     h->timbre.forward(z, cond, B, T, h->bridge.work);
+  });
+}
+
+int after_latent_map(after_handle h, int direction, const float* x, float* out, int B, int C_in, int T, int* C_out,
+                     void* stream) {
+  return guarded(h, [&] {
+    require_ready(h);
+    AFTER_REQUIRE(x && out, AFTER_EINVAL, "null tensor pointer");
+    BridgeScope bridge(h->bridge, stream);
+    h->latent_map.run(direction, x, out, B, C_in, T, C_out, h->bridge.work);
   });
 }
 

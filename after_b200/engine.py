@@ -140,8 +140,12 @@ class Engine:
                  drop_value: Optional[float] = None,
                  stream_slots: int = 0,
                  stream_max_frames: int = 0,
-                 stream_gn_frames: int = 0):
-        """``max_cache_size`` > 0 enables the streaming denoiser (what ``after_scripts/export.py:74-79`` binds to
+                 stream_gn_frames: int = 0,
+                 latent_map_state: Optional[Dict[str, torch.Tensor]] = None):
+        """``latent_map_state``: ``SmallAutoencoder.state_dict()`` of the export-time 2-D timbre projection
+        (after/diffusion/latent_plot.py:20-37) behind ``latent_map`` / ``Streamer.latent2map`` / ``map2latent``; without it
+        those are the identity the reference exports with ``--nolatent_project``.
+        ``max_cache_size`` > 0 enables the streaming denoiser (what ``after_scripts/export.py:74-79`` binds to
         LOCAL_ATTENTION_SIZE): one rolling KV history per ``cache_index`` in [0, max_steps).
         ``unet`` / ``unet_state``: a ``config.UNetConfig`` + ``UNET1D.state_dict()`` make the conv denoiser
         (after/diffusion/networks/unet1d.py) the engine's ``net`` instead of DenoiserV2: ``sample`` / ``model_forward`` then
@@ -182,6 +186,8 @@ class Engine:
                 if denoiser_state is not None:
                     raise ValueError("an engine carries one `net`: pass denoiser_state or unet_state, not both")
                 self._load(L.MODULE_UNET, unet_state)
+            if latent_map_state is not None:
+                self._load(L.MODULE_LATENT_MAP, latent_map_state)
             if any(s is not None for s in (denoiser_state, autoencoder_state, structure_state, timbre_state, unet_state)):
                 L.check(self._lib.after_finalize_weights(self._h, L.PRECISIONS[precision]), self._h,
                         "after_finalize_weights")
@@ -515,6 +521,18 @@ class Engine:
             L.check(self._lib.after_timbre_encode(self._h, z.data_ptr(), out.data_ptr(), B, T, self._stream()), self._h,
                     "after_timbre_encode")
         return out
+
+    def latent_map(self, x, direction: int):
+        """``Streamer.latent2map`` (direction 0) / ``map2latent`` (direction 1), after_scripts/export.py:494-508:
+        (B, C_in, T) -> (B, C_out, T): time average -> projection MLP (or identity) -> repeated over T."""
+        x = self._dev(x, "x")
+        B, Cin, T = x.shape
+        out = torch.empty(B, 64, T, device=self.device, dtype=torch.float32)
+        c_out = C.c_int(0)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.after_latent_map(self._h, int(direction), x.data_ptr(), out.data_ptr(), B, Cin, T, C.byref(c_out),
+                                               self._stream()), self._h, "after_latent_map")
+        return out.view(-1)[:B * c_out.value * T].view(B, c_out.value, T)
 
     def generate(self, audio_structure, audio_timbre, x0, nb_steps, guidance_timbre=1.0, guidance_structure=1.0):
         """Whole audio-to-audio chain on device tensors: (B,1,S) x2 + prior noise (B,C,S/ratio) -> audio (B,1,S)."""

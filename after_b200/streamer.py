@@ -11,7 +11,8 @@ the denoiser keeps one rolling KV history per diffusion step (``export.py:398-41
 corresponding stage processes each buffer on its own with the offline kernels (what the reference computes with
 ``cc.use_cached_conv(False)``).  A freshly created engine starts from zero state; the exported ``.ts`` starts from the state
 its export script left behind after its silent test passes -- ``prime_like_export()`` replays those.
-TorchScript serialisation (``export_to_ts``) and the latent-map MLP (``latent2map`` / ``map2latent``) are out of scope.
+TorchScript serialisation (``export_to_ts``) and the export-time TRAINING of the latent-map projection are out of scope;
+``latent2map`` / ``map2latent`` apply a given projection (``Engine(latent_map_state=...)``) or the identity.
 """
 from __future__ import annotations
 
@@ -185,9 +186,13 @@ class Streamer:
     __call__ = forward
 
     def latent2map(self, x):
-        raise NotImplementedError("latent-map MLP (after/diffusion/latent_plot.py) is an export-time UI artefact: out of scope")
+        """export.py:503-508: time average of the timbre latent -> ``project_model.encoder`` -> repeated over the buffer
+        (the identity without a projection, as exported with ``--nolatent_project``)."""
+        return self.engine.latent_map(x, 0)
 
-    map2latent = latent2map
+    def map2latent(self, x):
+        """export.py:496-501: time average of the 2-D map position -> ``project_model.decoder`` -> repeated."""
+        return self.engine.latent_map(x, 1)
 
 
 class MidiStreamer:
@@ -287,6 +292,10 @@ class MidiStreamer:
         return self.decode(self.diffuse(x, noise))
 
     def latent2map(self, x):
-        raise NotImplementedError("latent-map MLP (after/diffusion/latent_plot.py) is an export-time UI artefact: out of scope")
+        """export.py:503-508: time average of the timbre latent -> ``project_model.encoder`` -> repeated over the buffer
+        (the identity without a projection, as exported with ``--nolatent_project``)."""
+        return self.engine.latent_map(x, 0)
 
-    map2latent = latent2map
+    def map2latent(self, x):
+        """export.py:496-501: time average of the 2-D map position -> ``project_model.decoder`` -> repeated."""
+        return self.engine.latent_map(x, 1)

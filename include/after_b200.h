@@ -60,6 +60,7 @@ extern "C" {
 #define AFTER_MODULE_STRUCTURE_ENCODER 2 /* RectifiedFlow.encoder_time: Encoder1D state_dict   */
 #define AFTER_MODULE_TIMBRE_ENCODER 3    /* RectifiedFlow.encoder    : ECAPATDNN state_dict    */
 #define AFTER_MODULE_UNET 4              /* RectifiedFlow.net        : UNET1D state_dict (instead of DenoiserV2) */
+#define AFTER_MODULE_LATENT_MAP 5        /* Streamer.project_model   : SmallAutoencoder state_dict (optional) */
 
 /* classifier-free-guidance row layouts */
 #define AFTER_CFG_AUDIO 0 /* (cond,tc)/(drop,tc)/(drop,drop), f = g_t/max(g_s,clamp)  model.py:730-759 */
@@ -251,6 +252,15 @@ int after_structure_encode(after_handle h, const float* z, float* time_cond, int
 
 /* ECAPATDNN.forward (ecapa_encoder.py:567-624), the timbre encoder: z dev (B,C,T) -> cond dev (B,zt). */
 int after_timbre_encode(after_handle h, const float* z, float* cond, int B, int T, void* stream);
+
+/* Streamer.latent2map / map2latent of the exported model (after_scripts/export.py:494-508): the input is averaged over
+ * time, sent through the encoder (direction 0, latent2map) or decoder (direction 1, map2latent) half of the export-time
+ * projection (after/diffusion/latent_plot.py:20-37, loaded as AFTER_MODULE_LATENT_MAP: encoder.{0,2,4}.{weight,bias},
+ * decoder.{0,2,4}.{weight,bias}) and repeated over the buffer.  A handle without those tensors applies the identity the
+ * reference exports with --nolatent_project (export.py:143).  x dev (B,C_in,T) -> out dev (B,*C_out,T); out must hold
+ * B * 64 * T floats at most (layers are at most 64 wide); *C_out (may be NULL) receives the output channel count. */
+int after_latent_map(after_handle h, int direction, const float* x, float* out, int B, int C_in, int T, int* C_out,
+                     void* stream);
 
 /* The whole audio-to-audio chain of the notebooks (notebooks/audio_to_audio_demo.ipynb cells 5/19):
  *   z_s = encode(audio_structure); z_t = encode(audio_timbre); time_cond = encoder_time(z_s); cond = encoder(z_t);

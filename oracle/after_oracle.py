@@ -564,3 +564,21 @@ def unet1d_forward(sd: StateDict, cfg, x: Tensor, time: Tensor, cond: Optional[T
         if (p + ".self_attn.norm.weight") in sd:
             x = _self_attention_1d(sd, p + ".self_attn", x, 4)
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D timbre map of the exported model: Streamer.latent2map / map2latent (after_scripts/export.py:494-508) over the
+# export-time projection (after/diffusion/latent_plot.py:20-37: Linear-GELU-Linear-GELU-Linear).  Pinned against the
+# reference module by tests/golden/latent_map.npz (tests/golden/make_golden_latent_map.py).
+# ---------------------------------------------------------------------------------------------------------------------
+def latent_map(sd, x, direction):
+    """direction 0 = latent2map (``project_model.encoder``), 1 = map2latent (``project_model.decoder``); ``sd`` None is the
+    identity projection of ``--nolatent_project`` (export.py:143).  x (B, C_in, T) -> (B, C_out, T)."""
+    v = x.mean(-1)
+    if sd is not None:
+        half = "encoder" if direction == 0 else "decoder"
+        for i in (0, 2, 4):
+            v = F.linear(v, sd[f"{half}.{i}.weight"], sd[f"{half}.{i}.bias"])
+            if i < 4:
+                v = F.gelu(v)
+    return v.unsqueeze(-1).repeat(1, 1, x.shape[-1])

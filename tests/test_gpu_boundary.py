@@ -64,3 +64,31 @@ def test_engine_from_run_with_torchscript_codec(tmp_path):
         assert rel(eng.sample(x0.cuda(), cond.cuda(), tc.cuda(), 3, 2.0, 1.0), O.sample(den, mc.denoiser, x0, cond, tc, 3, 2.0, 1.0)) < 2e-4
     finally:
         eng.close()
+
+
+def test_latent_map_matches_reference_fixture_and_identity(golden):
+    """after_latent_map (Streamer.latent2map / map2latent, export.py:494-508) against the reference projection's outputs,
+    and the identity projection of a handle without AFTER_MODULE_LATENT_MAP tensors."""
+    import torch
+    from after_b200 import config, synth
+    from after_b200.engine import Engine
+    g = golden("latent_map")
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    mc = config.get_config("tiny")
+    den = synth.denoiser_state_dict(mc.denoiser, 0)
+    eng = Engine(model=mc, denoiser_state=den, precision="fp32", max_batch=1, max_steps=1, seq_len=8, latent_map_state=sd)
+    plain = Engine(model=mc, denoiser_state=den, precision="fp32", max_batch=1, max_steps=1, seq_len=8)
+    try:
+        l2m = eng.latent_map(torch.from_numpy(g["latents"]).cuda(), 0)
+        m2l = eng.latent_map(torch.from_numpy(g["maps"]).cuda(), 1)
+        assert l2m.shape == g["latent2map"].shape and m2l.shape == g["map2latent"].shape
+        assert torch.allclose(l2m.cpu(), torch.from_numpy(g["latent2map"]), atol=2e-6, rtol=1e-5)
+        assert torch.allclose(m2l.cpu(), torch.from_numpy(g["map2latent"]), atol=2e-6, rtol=1e-5)
+        x = torch.from_numpy(g["maps"]).cuda()
+        ident = plain.latent_map(x, 1)
+        assert torch.allclose(ident, x.mean(-1, keepdim=True).expand_as(x), atol=1e-6)
+        with pytest.raises(Exception):
+            eng.latent_map(torch.zeros(1, 5, 4).cuda(), 0)  # wrong channel count for the loaded projection
+    finally:
+        eng.close()
+        plain.close()

@@ -166,3 +166,15 @@ def test_unet1d_matches_reference(golden, tag):
     out64 = O.unet1d_forward(sd, cfg, T(g["x"]).double(), T(g["time"]).double(), cond.double() if cond is not None else None,
                              T(g["time_cond"]).double())
     assert rel(g["out"], out64) < 2e-5
+
+
+def test_latent_map_matches_reference(golden):
+    """Streamer.latent2map / map2latent: the oracle restatement against the reference SmallAutoencoder's outputs."""
+    g = golden("latent_map")
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    l2m = O.latent_map(sd, torch.from_numpy(g["latents"]), 0)
+    m2l = O.latent_map(sd, torch.from_numpy(g["maps"]), 1)
+    assert torch.allclose(l2m, torch.from_numpy(g["latent2map"]), atol=1e-6, rtol=1e-5)
+    assert torch.allclose(m2l, torch.from_numpy(g["map2latent"]), atol=1e-6, rtol=1e-5)
+    ident = O.latent_map(None, torch.from_numpy(g["maps"]), 0)
+    assert torch.allclose(ident, torch.from_numpy(g["maps"]).mean(-1, keepdim=True).expand_as(ident))
