@@ -192,7 +192,7 @@ struct Denoiser {
     map_src = arena->alloc<int>(maxN); map_trow = arena->alloc<int>(maxN);
     map_tstride = arena->alloc<int>(maxN); map_crow = arena->alloc<int>(maxN);
     guidance = arena->alloc<float>(4);
-    flag_stride = maxN * ceil_div(maxT, 2 * tc::BM);
+    flag_stride = 2 * maxN * ceil_div(maxT, 2 * tc::BM);  // two counters per row block (launch_mlp_fused)
     mlp_flags = arena->alloc<int>((size_t)L * flag_stride);
 #ifdef AFTER_DEBUG
     {  // opt-in dynamic shared memory of the staged A/B variant (must not first happen inside a stream capture)

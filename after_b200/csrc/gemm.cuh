@@ -985,10 +985,18 @@ struct LinearProblem {
 };
 
 // Work list of cluster `cluster_id`: its up-projection tiles (prob 0) first, then down-projection items (prob 1 =
-// first / only K part, prob 2 = second K half); item j of problem 1 is output tile j / ksplit, so both halves of a
-// tile, and the tiles of the row blocks that complete first, come first.
-__device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters, int n0, int n1, int ksplit, int& prob,
-                                           int& tile) {
+// first / only K part, prob 2 = second K half).
+// groups == 1: item j of problem 1 is output tile j / ksplit, so both halves of a tile, and the tiles of the row blocks
+// that complete first, come first; a down item waits for ALL up tiles of its row block.
+// groups == 2 (ksplit == 2, an even number of up N tiles): the up tiles are walked N-half-major -- every row block's tiles
+// of the first half of the hidden columns, then every row block's tiles of the second half -- and the down items K-half-
+// major; a down item of K half g waits only for the up tiles of N half g of its row block (counter flags[2 mt + g]).  After
+// the first round of up tiles EVERY first-half down item is ready, instead of the items of the first half of the row
+// blocks, so fewer clusters sit out the last up epilogues: +1 % (fp32 mode) / +2.8 % (bf16 mode) steps/s, bitwise identical
+// results (profiles/r02x_ab_mlp_groups.jsonl).  (K thirds with three groups balance the clusters -- every one ends 45-48 us
+// after the start instead of 44-51 -- but the third partial tensor costs what that gains: profiles/r02y_ab_mlp_k3.jsonl.)
+__device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters, int n0, int n1, int ksplit, int groups,
+                                           int& prob, int& tile) {
   const int mine0 = cluster_id < n0 ? (n0 - cluster_id + n_clusters - 1) / n_clusters : 0;
   if (i < mine0) {
     prob = 0;
@@ -997,11 +1005,28 @@ __device__ __forceinline__ bool fused_item(int i, int cluster_id, int n_clusters
   }
   const int j = (n_clusters - 1 - cluster_id) + (i - mine0) * n_clusters;  // lightest clusters take problem 1 first
   if (j < n1 * ksplit) {
-    prob = 1 + (j % ksplit);
-    tile = j / ksplit;
+    if (groups == 2) {
+      prob = 1 + j / n1;
+      tile = j % n1;
+    } else {
+      prob = 1 + (j % ksplit);
+      tile = j / ksplit;
+    }
     return true;
   }
   return false;
+}
+// (row block, N tile) of up-projection tile index `tile`; with 2 groups the index runs N-half-major (see fused_item)
+__device__ __forceinline__ void up_tile_coords(int tile, int n_tiles_n, int n_tiles, int groups, int& mt, int& nt) {
+  if (groups == 2) {
+    const int h = n_tiles_n >> 1, per_group = n_tiles >> 1;  // N tiles per half and row block; tiles per half
+    const int g = tile >= per_group ? 1 : 0, r = tile - g * per_group;
+    mt = r / h;
+    nt = g * h + (r - mt * h);
+  } else {
+    nt = tile % n_tiles_n;
+    mt = tile / n_tiles_n;
+  }
 }
 
 // One more warp than the pair kernel: warp 2 + EPI_WARPS publishes finished up-projection tiles (see below).
@@ -1010,7 +1035,7 @@ constexpr int NUM_THREADS_MLP = NUM_THREADS2 + 32;
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS_MLP, 1)
 mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_constant__ LinearProblem p1, int T, int nprod,
-                     int m_tiles_per_b, int* __restrict__ flags, int flag_need, unsigned long long* dbg) {
+                     int m_tiles_per_b, int* __restrict__ flags, int flag_need, int flag_groups, unsigned long long* dbg) {
   auto mark = [&](int slot) {  // profiling experiments only: per-cluster %globaltimer marks of the leader CTA
     if (kDebugBuild && dbg && (blockIdx.x & 1) == 0) {
       unsigned long long t;
@@ -1071,18 +1096,21 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       int it = 0, prob, tile;
-      for (int i = 0; fused_item(i, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++i) {
+      for (int i = 0; fused_item(i, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, flag_groups, prob, tile); ++i) {
         const LinearProblem& p = prob ? p1 : p0;
-        const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        int nt, mt;
+        if (prob == 0) up_tile_coords(tile, p0.n_tiles_n, p0.n_tiles, flag_groups, mt, nt);
+        else { nt = tile % p1.n_tiles_n; mt = tile / p1.n_tiles_n; }
         const int b = mt / m_tiles_per_b;
         const int t0 = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM;
         const int nrow = nt * BN + (int)rank * (BN / 2);
         if (prob >= 1) {  // the hidden activations of row block mt must be complete and visible to the async proxy
+          const int* flag = flags + (flag_groups == 2 ? 2 * mt + (prob - 1) : mt);
           mark(1);
           int seen;
           long long t_start = clock64();
           do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + mt) : "memory");
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
             if (seen < flag_need && clock64() - t_start > 4000000000LL) {
               printf("after_b200: fused MLP dependency wait timeout (cluster %d, row block %d: %d of %d)\n", cluster_id, mt, seen, flag_need);
               __trap();
@@ -1114,7 +1142,7 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc2(BN);
       int it = 0, prob, tile;
-      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++ti) {
+      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, flag_groups, prob, tile); ++ti) {
         const int nkb = prob ? p1.Cin / BK / p1.ksplit : p0.Cin / BK;
         const int buf = ti & 1;
         mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
@@ -1152,21 +1180,24 @@ mlp_fused_tc2_kernel(const __grid_constant__ LinearProblem p0, const __grid_cons
     // consumer's ld.acquire.gpu.
     if (lane == 0) {
       int prob, tile;
-      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile) && prob == 0; ++ti) {
-        const int mt = tile / p0.n_tiles_n;
+      for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, flag_groups, prob, tile) && prob == 0; ++ti) {
+        int mt, nt;
+        up_tile_coords(tile, p0.n_tiles_n, p0.n_tiles, flag_groups, mt, nt);
+        int* flag = flags + (flag_groups == 2 ? 2 * mt + (nt >= (p0.n_tiles_n >> 1) ? 1 : 0) : mt);
         mbar_wait(&pub_bar[ti & 1], (ti >> 1) & 1);
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flags + mt) : "memory");
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
       }
     }
   } else {
     const int quad = warp & 3;
     const uint32_t te0 = mapa(smem_u32(&tmem_empty[0]), 0), te1 = mapa(smem_u32(&tmem_empty[1]), 0);
     int prob, tile;
-    for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, prob, tile); ++ti) {
-      const LinearProblem& p = prob ? p1 : p0;
+    for (int ti = 0; fused_item(ti, cluster_id, n_clusters, p0.n_tiles, p1.n_tiles, p1.ksplit, flag_groups, prob, tile); ++ti) {
       const GemmEpi& pe1 = prob == 2 ? p1.epi2 : p1.epi;
-      const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      int nt, mt;
+      if (prob == 0) up_tile_coords(tile, p0.n_tiles_n, p0.n_tiles, flag_groups, mt, nt);
+      else { nt = tile % p1.n_tiles_n; mt = tile / p1.n_tiles_n; }
       const int b = mt / m_tiles_per_b;
       const int t_base = (mt % m_tiles_per_b) * (2 * BM) + (int)rank * BM + quad * 32;
       const int n0 = nt * BN;

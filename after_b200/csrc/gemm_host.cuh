@@ -283,6 +283,11 @@ inline int mlp_ksplit() {
 // `partial`: when non-null and the K-split is on, receives the second K half of the down projection ([B*T, ldo] fp32,
 // no bias / residual); the caller adds it to epi1.out_f32 when it next reads that tensor.  *used_partial says whether
 // it was written.
+inline int mlp_flag_groups() {  // AFTER_MLP_FLAG_GROUPS=1 (debug builds): one dependency counter per row block, for A/B runs
+  static int v = -1;
+  if (v < 0) { const char* e = debug_env("AFTER_MLP_FLAG_GROUPS"); v = (e && e[0] == '1') ? 1 : 2; }
+  return v;
+}
 inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi0, ActOperand& hid, const GemmWeight& W2,
                              GemmEpi epi1, int B, int T, int precision, int* flags, cudaStream_t st,
                              float* partial = nullptr, bool* used_partial = nullptr) {
@@ -347,8 +352,12 @@ inline bool launch_mlp_fused(ActOperand& a_in, const GemmWeight& W0, GemmEpi epi
     dbg_now = dbg;
     AFTER_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 128 * 16 * sizeof(unsigned long long), st));
   }
+  // dependency counters per (row block, half of the hidden columns) when the down projection is K-split in two and the up
+  // projection has an even number of N tiles: a K half of a down item then waits for its half of the up tiles only, and the
+  // work list runs half-major (fused_item); else one counter per row block.  flags holds 2 ints per row block either way.
+  const int groups = (p1.ksplit == 2 && p0.n_tiles_n % 2 == 0 && mlp_flag_groups() == 2) ? 2 : 1;
   launch_k(tc::mlp_fused_tc2_kernel<BN>, dim3(2 * clusters), dim3(tc::NUM_THREADS_MLP), (size_t)smem, st, p0, p1, T, nprod,
-           m_tiles_per_b, flags, 2 * p0.n_tiles_n, dbg_now);
+           m_tiles_per_b, flags, 2 * p0.n_tiles_n / groups, groups, dbg_now);
   AFTER_COUNT_LAUNCH();
   if (dbg_now) {
     AFTER_CUDA_CHECK(cudaStreamSynchronize(st));
