@@ -63,6 +63,9 @@ class OracleEngine:
     def timbre_encode(self, z):
         return O.ecapa_forward(self.sd_te, self.te_cfg, z)
 
+    def latent_map(self, x, direction):
+        return O.latent_map(getattr(self, "sd_map", None), x, direction)
+
     def sample(self, x0, cond, tc, nb_steps, g_t=1.0, g_s=1.0, cfg_variant=L.CFG_AUDIO, clamp=0.01):
         self.calls.append(("sample", cfg_variant, clamp, nb_steps, g_t, g_s))
         return O.sample(self.sd_den, self.den_cfg, x0, cond, tc, nb_steps, g_t, g_s, cfg_variant=cfg_variant, clamp=clamp)
@@ -114,8 +117,10 @@ def test_audio_streamer_methods_buffers_and_attributes():
     assert rel(out[:1], want) < 1e-5
     with pytest.raises(ValueError):
         st.diffuse(torch.zeros(1, 5, 4))
-    with pytest.raises(NotImplementedError):
-        st.latent2map(torch.zeros(1, 2, 8))
+    # without a projection the exported model's latent2map / map2latent are the time average repeated (export.py:143, 494-508)
+    m = torch.arange(16.0).view(1, 2, 8)
+    assert torch.equal(st.latent2map(m), m.mean(-1, keepdim=True).expand(1, 2, 8))
+    assert torch.equal(st.map2latent(m), st.latent2map(m))
 
 
 def test_streaming_engine_routes_to_sample_stream():
