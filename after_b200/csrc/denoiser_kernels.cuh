@@ -375,8 +375,8 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
 //     butterfly (5 shuffles for 4 sums instead of 16); afterwards lane l holds the score of query (l >> 2) & 3 only, so the
 //     softmax state is MAXK registers per lane, not 4 MAXK; the probabilities travel back by 4 shuffles per key.
 //   * LayerNorm statistics span the NH / 2 warps of the chunk: per-warp partials of the 4 queries (6-shuffle transposing
-//     reduction) are exchanged through shared memory under a named barrier of the chunk's warps only (4 exchanges:
-//     mean / centred second moment of LN2, then of LN3 -- the same two-pass statistics as everywhere else).
+//     reduction) are exchanged through shared memory under a named barrier of the chunk's warps only, once per norm:
+//     per-warp mean and centred second moment, combined exactly (no E[x^2] - mean^2 cancellation).
 // Blocks hold CPB consecutive chunks so that the 7 history rows two neighbouring chunks share are L1 hits.
 // Key / value rows are read UNCONDITIONALLY for j < MAXK (one LDG with an immediate offset each, no predicate, no zero
 // fill): rows past the chunk end are masked in the softmax and skipped in P.V (a warp-uniform test), so they only have to
@@ -539,34 +539,46 @@ attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_ou
     x[r] = make_float4(fmaf(o[r].x, inv, res[r].x), fmaf(o[r].y, inv, res[r].y), fmaf(o[r].z, inv, res[r].z),
                        fmaf(o[r].w, inv, res[r].w));
   }
-  // LayerNorm statistics of the 4 query rows over the chunk's WPC warps with ONE exchange per norm: every warp reduces
-  // its 128 columns to (sum, sum of squares); var = E[x^2] - mean^2 (biased, as nn.LayerNorm).  The rows are O(1) with
-  // |mean| <~ std here (outputs of an AdaLN), so the one-pass form costs ~1e-7 relative, far inside the 1e-3 budget.
+  // LayerNorm statistics of the 4 query rows over the chunk's WPC warps with ONE exchange per norm, and exact: every warp
+  // reduces its 128 columns to (mean_w, M2_w = sum of squares about mean_w), the pairs are combined by the parallel-variance
+  // identity (Chan et al.):  mean = avg(mean_w),  M2 = sum(M2_w) + 128 * sum((mean_w - mean)^2),  var = M2 / D  (biased, as
+  // nn.LayerNorm).  No E[x^2] - mean^2 cancellation, whatever the row's offset.
   auto hsum = [](const float4& v) { return (v.x + v.y) + (v.z + v.w); };
-  auto hsq = [](const float4& v) { return fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))); };
+  auto hsq = [](const float4& v, float mu) {
+    const float a = v.x - mu, b = v.y - mu, c = v.z - mu, d = v.w - mu;
+    return fmaf(a, a, fmaf(b, b, fmaf(c, c, d * d)));
+  };
   auto group_stats = [&](int which, float (&mean)[4], float (&rstd)[4]) {
-    const float s1 = warp_reduce4(hsum(x[0]), hsum(x[1]), hsum(x[2]), hsum(x[3]), lane);
-    const float s2 = warp_reduce4(hsq(x[0]), hsq(x[1]), hsq(x[2]), hsq(x[3]), lane);
-    if ((lane & 7) == 0) {  // the lane holds the totals of query lane >> 3
-      red[cib][which][0][w][lane >> 3] = s1;
-      red[cib][which][1][w][lane >> 3] = s2;
+    const float mw = warp_reduce4(hsum(x[0]), hsum(x[1]), hsum(x[2]), hsum(x[3]), lane) * (1.0f / 128.0f);
+    float mu[4];  // this warp's mean of row r lives in the lanes 8 r .. 8 r + 7
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mu[r] = __shfl_sync(0xffffffffu, mw, 8 * r);
+    const float m2 = warp_reduce4(hsq(x[0], mu[0]), hsq(x[1], mu[1]), hsq(x[2], mu[2]), hsq(x[3], mu[3]), lane);
+    if ((lane & 7) == 0) {
+      red[cib][which][0][w][lane >> 3] = mw;
+      red[cib][which][1][w][lane >> 3] = m2;
     }
     asm volatile("bar.sync %0, %1;" ::"r"(cib + 1), "r"(WPC * 32) : "memory");
-    float4 t1 = *reinterpret_cast<const float4*>(&red[cib][which][0][0][0]);
-    float4 t2 = *reinterpret_cast<const float4*>(&red[cib][which][1][0][0]);
+    float4 mws[WPC];
+    mws[0] = *reinterpret_cast<const float4*>(&red[cib][which][0][0][0]);
+    float4 tm = mws[0], t2 = *reinterpret_cast<const float4*>(&red[cib][which][1][0][0]);
 #pragma unroll
     for (int i = 1; i < WPC; ++i) {
-      const float4 p1 = *reinterpret_cast<const float4*>(&red[cib][which][0][i][0]);
-      const float4 p2 = *reinterpret_cast<const float4*>(&red[cib][which][1][i][0]);
-      t1.x += p1.x; t1.y += p1.y; t1.z += p1.z; t1.w += p1.w;
-      t2.x += p2.x; t2.y += p2.y; t2.z += p2.z; t2.w += p2.w;
+      mws[i] = *reinterpret_cast<const float4*>(&red[cib][which][0][i][0]);
+      const float4 q2 = *reinterpret_cast<const float4*>(&red[cib][which][1][i][0]);
+      tm.x += mws[i].x; tm.y += mws[i].y; tm.z += mws[i].z; tm.w += mws[i].w;
+      t2.x += q2.x; t2.y += q2.y; t2.z += q2.z; t2.w += q2.w;
     }
-    const float a1[4] = {t1.x, t1.y, t1.z, t1.w}, a2[4] = {t2.x, t2.y, t2.z, t2.w};
+    mean[0] = tm.x * (1.0f / WPC); mean[1] = tm.y * (1.0f / WPC); mean[2] = tm.z * (1.0f / WPC); mean[3] = tm.w * (1.0f / WPC);
+    float dev[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      mean[r] = a1[r] * (1.0f / (float)D);
-      rstd[r] = rsqrt_approx(fmaf(a2[r], 1.0f / (float)D, fmaf(-mean[r], mean[r], 1e-5f)));
+    for (int i = 0; i < WPC; ++i) {
+      const float d0 = mws[i].x - mean[0], d1 = mws[i].y - mean[1], d2 = mws[i].z - mean[2], d3 = mws[i].w - mean[3];
+      dev[0] = fmaf(d0, d0, dev[0]); dev[1] = fmaf(d1, d1, dev[1]); dev[2] = fmaf(d2, d2, dev[2]); dev[3] = fmaf(d3, d3, dev[3]);
     }
+    const float tt[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rstd[r] = rsqrt_approx(fmaf(dev[r], 128.0f, tt[r]) * (1.0f / (float)D) + 1e-5f);
   };
   float mean[4], rstd[4];
   group_stats(0, mean, rstd);
