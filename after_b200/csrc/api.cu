@@ -503,8 +503,7 @@ static void generate_device(after_handle h, const float* a_s, const float* a_t, 
   float* x = z_t + nz;
   float* tcond = x + nz;
   float* cond = tcond + ntc;
-  h->codec.encode(a_s, z_s, B, samples, st);
-  h->codec.encode(a_t, z_t, B, samples, st);
+  h->codec.encode_pair(a_s, a_t, z_s, z_t, B, samples, st);  // both inputs as one batch of 2 B chunks
   h->structure.forward(z_s, tcond, B, T, st);
   h->timbre.forward(z_t, cond, B, T, st);
   h->denoiser.sample(x0, cond, tcond, x, B, T, nb_steps, g_t, g_s, AFTER_CFG_AUDIO, 0.01f, st);

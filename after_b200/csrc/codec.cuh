@@ -153,6 +153,7 @@ struct ConvNet {
   size_t slot_doubles = 0;
   size_t buf_elems = 0, op_elems = 0;
   int maxB = 0;
+  int wsB = 0;  // chunks the offline workspace holds (Codec: 2 x max_batch for encode_pair; 0 = maxB)
   GraphCache graphs;
 
   const HostTensor& get(const std::string& key) const {
@@ -663,9 +664,13 @@ struct Codec : ConvNet {
       mxp = std::max(mxp, T * (size_t)std::max(dch[i], 64));
       if (i < n_stages) T *= c.ae_factors[n_stages - 1 - i];
     }
-    alloc_workspace(mx, mxp, c.max_batch, 4 * (n_stages * nb + 4) + 16);
-    io_audio = arena->alloc<float>((size_t)c.max_batch * c.ae_max_samples);
-    io_z = arena->alloc<float>((size_t)c.max_batch * c.ae_z_channels * (c.ae_max_samples / ratio));
+    // the workspace holds 2 x max_batch chunks: the audio-to-audio chain encodes its structure and timbre inputs as ONE
+    // batch (encode_pair) -- the encoder's kernels are launch- and latency-bound at 8 chunks (profiles/r01c_codec_sweep.jsonl)
+    alloc_workspace(mx, mxp, 2 * c.max_batch, 4 * (n_stages * nb + 4) + 16);
+    maxB = c.max_batch;  // the public limit (and the size of the streaming state) stays max_batch; wsB = what the workspace holds
+    wsB = 2 * c.max_batch;
+    io_audio = arena->alloc<float>((size_t)2 * c.max_batch * c.ae_max_samples);
+    io_z = arena->alloc<float>((size_t)2 * c.max_batch * c.ae_z_channels * (c.ae_max_samples / ratio));
 
     // ---- streaming export (after_scripts/export_autoencoder.py:16-153, 305-319: AE_notcausal = cached encoder + offline
     // decoder over [z_buffer ; z] with overlap-add, CachedGroupNorm.stream = True in both)
@@ -772,6 +777,20 @@ struct Codec : ConvNet {
     AFTER_CUDA_CHECK(cudaMemcpyAsync(io_audio, audio, (size_t)B * samples * sizeof(float), cudaMemcpyDeviceToDevice, st));
     graphs.run({0, B, (int)(samples & 0x7fffffff)}, st, [&] { encode_body(io_audio, io_z, B, samples, st); });
     AFTER_CUDA_CHECK(cudaMemcpyAsync(z, io_z, (size_t)B * cfg.ae_z_channels * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+
+  // two encode calls with the same B and length as one batch of 2 B chunks: z1 = encode(audio1), z2 = encode(audio2)
+  // (chunks are independent in every kernel of the encoder, GroupNorm statistics are per chunk)
+  void encode_pair(const float* audio1, const float* audio2, float* z1, float* z2, int B, int64_t samples, cudaStream_t st) {
+    check(B, samples);
+    AFTER_REQUIRE(2 * B <= wsB, AFTER_ESTATE, "codec workspace does not hold 2 x B chunks");
+    const int T = (int)(samples / ratio);
+    const size_t na = (size_t)B * samples, nz = (size_t)B * cfg.ae_z_channels * T;
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_audio, audio1, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(io_audio + na, audio2, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    graphs.run({0, 2 * B, (int)(samples & 0x7fffffff)}, st, [&] { encode_body(io_audio, io_z, 2 * B, samples, st); });
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(z1, io_z, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    AFTER_CUDA_CHECK(cudaMemcpyAsync(z2, io_z + nz, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
 
   // ------------------------------------------------------------------ AutoEncoder.decode
