@@ -379,9 +379,10 @@ attn_warp_chunk_kernel(const float* __restrict__ qkv, float* h, RowOperandOut a_
 //     per-warp mean and centred second moment, combined exactly (no E[x^2] - mean^2 cancellation).
 // Blocks hold CPB consecutive chunks so that the 7 history rows two neighbouring chunks share are L1 hits.
 // Key / value rows are read UNCONDITIONALLY for j < MAXK (one LDG with an immediate offset each, no predicate, no zero
-// fill): rows past the chunk end are masked in the softmax and skipped in P.V (a warp-uniform test), so they only have to
-// be readable -- the next frames of the sequence, the next sequence, or the 32 pad rows behind the QKV buffer
-// (Denoiser::finalize).
+// fill): rows past the chunk end are masked in the softmax, so they only have to be readable -- the next frames of the
+// sequence, the next sequence, or the 32 pad rows behind the QKV buffer (Denoiser::finalize).  Value rows past the chunk
+// end re-read the chunk's last row instead (their probability is exactly 0, but 0 * inf is not 0 and a stale row may hold
+// anything).
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float head_reduce4(float a0, float a1, float a2, float a3) {
   // Sums over the 16 lanes of a half-warp of four per-query partials held in LANE-PERMUTED order: a_i of lane l belongs
@@ -508,7 +509,7 @@ attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_ou
     float4 vv[KB];
 #pragma unroll
     for (int j = 0; j < KB; ++j)
-      vv[j] = load_qkv4(vp + (size_t)(b0 + j) * (3 * D));
+      vv[j] = load_qkv4(vp + (size_t)min(b0 + j, nk - 1) * (3 * D));  // rows >= nk: a live row again (p = 0 needs a finite v)
     if (b0 + KB >= MAXK) {
       // everything the tail needs is requested together with the last value rows: one more round trip saved
 #pragma unroll
@@ -520,7 +521,6 @@ attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_ou
     }
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      if (b0 + j >= nk) continue;  // warp-uniform; stale rows past the chunk end may hold anything (0 * inf is not 0)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const float p = __shfl_sync(0xffffffffu, sc[b0 + j], hb + 4 * r);
@@ -559,26 +559,26 @@ attn_chunk_group_kernel(const QT* __restrict__ qkv, float* h, RowOperandOut a_ou
       red[cib][which][1][w][lane >> 3] = m2;
     }
     asm volatile("bar.sync %0, %1;" ::"r"(cib + 1), "r"(WPC * 32) : "memory");
-    float4 mws[WPC];
-    mws[0] = *reinterpret_cast<const float4*>(&red[cib][which][0][0][0]);
-    float4 tm = mws[0], t2 = *reinterpret_cast<const float4*>(&red[cib][which][1][0][0]);
-#pragma unroll
-    for (int i = 1; i < WPC; ++i) {
-      mws[i] = *reinterpret_cast<const float4*>(&red[cib][which][0][i][0]);
-      const float4 q2 = *reinterpret_cast<const float4*>(&red[cib][which][1][i][0]);
-      tm.x += mws[i].x; tm.y += mws[i].y; tm.z += mws[i].z; tm.w += mws[i].w;
-      t2.x += q2.x; t2.y += q2.y; t2.z += q2.z; t2.w += q2.w;
-    }
-    mean[0] = tm.x * (1.0f / WPC); mean[1] = tm.y * (1.0f / WPC); mean[2] = tm.z * (1.0f / WPC); mean[3] = tm.w * (1.0f / WPC);
-    float dev[4] = {0.f, 0.f, 0.f, 0.f};
+    // lane l combines the WPC pairs of query l & 3 (all lanes in step, 8 scalar loads), the four results are gathered by
+    // shuffles: ~40 instructions instead of ~140 when every lane combined all four queries
+    const int qq = lane & 3;
+    float mws[WPC], mq = 0.f, m2q = 0.f;
 #pragma unroll
     for (int i = 0; i < WPC; ++i) {
-      const float d0 = mws[i].x - mean[0], d1 = mws[i].y - mean[1], d2 = mws[i].z - mean[2], d3 = mws[i].w - mean[3];
-      dev[0] = fmaf(d0, d0, dev[0]); dev[1] = fmaf(d1, d1, dev[1]); dev[2] = fmaf(d2, d2, dev[2]); dev[3] = fmaf(d3, d3, dev[3]);
+      mws[i] = red[cib][which][0][i][qq];
+      mq += mws[i];
+      m2q += red[cib][which][1][i][qq];
     }
-    const float tt[4] = {t2.x, t2.y, t2.z, t2.w};
+    mq *= 1.0f / WPC;
+    float dev = 0.f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) rstd[r] = rsqrt_approx(fmaf(dev[r], 128.0f, tt[r]) * (1.0f / (float)D) + 1e-5f);
+    for (int i = 0; i < WPC; ++i) { const float d = mws[i] - mq; dev = fmaf(d, d, dev); }
+    const float rq_ = rsqrt_approx(fmaf(dev, 128.0f, m2q) * (1.0f / (float)D) + 1e-5f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      mean[r] = __shfl_sync(0xffffffffu, mq, r);
+      rstd[r] = __shfl_sync(0xffffffffu, rq_, r);
+    }
   };
   float mean[4], rstd[4];
   group_stats(0, mean, rstd);
