@@ -64,6 +64,7 @@ struct Denoiser {
   static constexpr int SKINNY_ROWS = 16;
   float *sk_a = nullptr, *sk_hid = nullptr;     // [SKINNY_ROWS][D], [SKINNY_ROWS][HID]
   bool skinny_now = false;
+  int cfg_streams = 0;  // > 0 while run_network works on a CFG batch of 3 x cfg_streams sequences (row order of launch_adaln_t)
   unsigned* stream_barrier = nullptr;           // grid-barrier counter of the persistent streaming-block kernel
   int n_sms = 0;
 
@@ -307,8 +308,14 @@ struct Denoiser {
   void launch_adaln_t(const float* hin, const float* hadd, int use_src, int l, int rows, int T, cudaStream_t st) {
     RowOperandOut o = operand_out(a_op);
     ProfScope prof(KC_ROW_NORM, st, 0.0, (double)rows * D * (tc_mode() ? 4.0 * 2 + 2.0 * (nprod() > 1 ? 2 : 1) : 12.0));
-    launch_k(adaln_t_ln1_kernel<NV>, dim3(ceil_div(rows, 8)), dim3(256), 0, st, hin, hadd, h, o, adaT, L * 2 * D, l * 2 * D, seqmap(),
-             use_src, layers[l].n1_g, layers[l].n1_b, rows, T);
+    // CFG batches (rows = 3 B T): groups 0 and 1 of a (stream, frame) go to neighbouring warps (see the kernel)
+    static int pair_off = -1;  // AFTER_ADALN_PAIR=0 (debug builds): plain row order, for A/B runs
+    if (pair_off < 0) { const char* e = debug_env("AFTER_ADALN_PAIR"); pair_off = (e && e[0] == '0') ? 1 : 0; }
+    const int Bs = cfg_streams;
+    const int pair_frames = (!pair_off && Bs > 0 && rows == 3 * Bs * T) ? Bs * T : 0;
+    const int blocks = pair_frames ? ceil_div(pair_frames, 4) + ceil_div(rows - 2 * pair_frames, 8) : ceil_div(rows, 8);
+    launch_k(adaln_t_ln1_kernel<NV>, dim3(blocks), dim3(256), 0, st, hin, hadd, h, o, adaT, L * 2 * D, l * 2 * D, seqmap(),
+             use_src, layers[l].n1_g, layers[l].n1_b, rows, T, pair_frames, Bs);
     AFTER_COUNT_LAUNCH();
   }
   template <int NH, int MAXK>
@@ -464,6 +471,7 @@ struct Denoiser {
   void run_network(const float* x_src, int n_src, int N, int T, const float* adaC_step, cudaStream_t st,
                    int cache_index = -1) {
     const int rows = N * T;
+    cfg_streams = (N == 3 * n_src) ? n_src : 0;
     PdlScope pdl(true);  // every kernel below starts with pdl_wait(): programmatic dependent launches are safe
     // a live streaming block is a dozen rows: weight-streaming fp32 linears instead of 256-row tensor-core tiles
     skinny_now = cache_index >= 0 && rows <= SKINNY_ROWS && sk_a != nullptr;
